@@ -1,0 +1,162 @@
+// etb_common.cuh -- shared host/device helpers of libembtab_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/embtab_b200.h"
+
+namespace etb {
+
+// ---------------------------------------------------------------- errors / bookkeeping
+char* error_buffer();  // thread-local, 512 bytes
+int32_t fail(int32_t status, const char* fmt, ...);
+int32_t& launch_counter();  // thread-local: kernels launched by the current API call
+
+#define ETB_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return ::etb::fail(ETB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,               \
+                               cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    } while (0)
+
+#define ETB_REQUIRE(cond, ...)                                                             \
+    do {                                                                                   \
+        if (!(cond)) return ::etb::fail(ETB_ERR_INVALID, __VA_ARGS__);                     \
+    } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define ETB_LAUNCHED()                                                                     \
+    do {                                                                                   \
+        ++::etb::launch_counter();                                                         \
+        ETB_CUDA(cudaGetLastError());                                                      \
+    } while (0)
+
+inline size_t elt_bytes(int32_t elt) { return (elt == ETB_F32 || elt == ETB_I32) ? 4 : 8; }
+inline bool elt_valid(int32_t elt) { return elt >= ETB_F32 && elt <= ETB_I64; }
+inline bool idx_elt_valid(int32_t e) { return e == ETB_I32 || e == ETB_I64; }
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+inline int pow2ceil(int x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+// ---------------------------------------------------------------- device table addressing
+// Compact device-side form of etb_table: the GPU `columnpointer`
+// (reference src/simple.jl:52-55, src/split.jl:59-65,81-86).
+struct DevTable {
+    const char* base;           // Simple
+    const char* const* chunks;  // Split (device array)
+    int64_t row_stride;         // bytes between embedding rows (ld * sizeof(T))
+    uint32_t shard_rows;        // 0 = Simple
+    uint32_t pad;
+};
+
+inline DevTable make_dev_table(const etb_table& t) {
+    DevTable d;
+    d.base = (const char*)t.base;
+    d.chunks = (const char* const*)t.chunks;
+    d.row_stride = (int64_t)t.ld * (int64_t)elt_bytes(t.elt);
+    d.shard_rows = t.chunks ? (uint32_t)t.shard_rows : 0u;
+    d.pad = 0;
+    return d;
+}
+
+int32_t validate_table(const etb_table& t, const char* who);
+
+#ifdef __CUDACC__
+// address of embedding row `i1` (1-based, as the host passes it)
+__device__ __forceinline__ const char* row_ptr(const DevTable& t, int64_t i1) {
+    uint64_t z = (uint64_t)(i1 - 1);
+    if (t.shard_rows == 0) return t.base + z * (uint64_t)t.row_stride;
+    uint64_t chunk, within;
+    if (z <= 0xffffffffull) {  // 32-bit divide is ~4x cheaper than the 64-bit one
+        uint32_t z32 = (uint32_t)z;
+        chunk = z32 / t.shard_rows;
+        within = z32 - (uint32_t)chunk * t.shard_rows;
+    } else {
+        chunk = z / t.shard_rows;
+        within = z - chunk * t.shard_rows;
+    }
+    return (const char*)__ldg((const unsigned long long*)t.chunks + chunk) + within * (uint64_t)t.row_stride;
+}
+
+__device__ __forceinline__ const char* shfl_ptr(const char* p, int src, int width) {
+    unsigned long long v = (unsigned long long)p;
+    unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src, width);
+    unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src, width);
+    return (const char*)(((unsigned long long)hi << 32) | lo);
+}
+
+// ---------------------------------------------------------------- vector access
+// A VB-byte register vector of NE = VB/sizeof(T) elements of T.
+template <typename T, int VB>
+struct alignas(VB) Vec {
+    static constexpr int NE = VB / (int)sizeof(T);
+    T e[NE];
+};
+
+// read-only, table rows: keep in L2 (Zipf reuse), do not pollute L1
+template <int VB>
+__device__ __forceinline__ void ld_row(void* out, const char* p);
+template <>
+__device__ __forceinline__ void ld_row<16>(void* out, const char* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    *(uint4*)out = v;
+}
+template <>
+__device__ __forceinline__ void ld_row<8>(void* out, const char* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    *(uint2*)out = v;
+}
+template <>
+__device__ __forceinline__ void ld_row<4>(void* out, const char* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    *(uint32_t*)out = v;
+}
+
+// streaming store (written once, not re-read by this kernel): the GPU analogue of the
+// reference's non-temporal stores (src/simd.jl:31-45)
+template <int VB>
+__device__ __forceinline__ void st_stream(char* p, const void* in);
+template <>
+__device__ __forceinline__ void st_stream<16>(char* p, const void* in) {
+    uint4 v = *(const uint4*)in;
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <>
+__device__ __forceinline__ void st_stream<8>(char* p, const void* in) {
+    uint2 v = *(const uint2*)in;
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+template <>
+__device__ __forceinline__ void st_stream<4>(char* p, const void* in) {
+    uint32_t v = *(const uint32_t*)in;
+    asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// plain (cacheable) vector load/store used for read-modify-write of table rows
+template <int VB>
+__device__ __forceinline__ void ld_plain(void* out, const char* p) {
+    if constexpr (VB == 16) *(uint4*)out = *(const uint4*)p;
+    else if constexpr (VB == 8) *(uint2*)out = *(const uint2*)p;
+    else *(uint32_t*)out = *(const uint32_t*)p;
+}
+
+template <typename IdxT>
+__device__ __forceinline__ int64_t ld_index(const void* idx, int64_t pos) {
+    return (int64_t)__ldg((const IdxT*)idx + pos);
+}
+#endif  // __CUDACC__
+
+}  // namespace etb

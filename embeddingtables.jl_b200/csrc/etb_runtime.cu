@@ -1,0 +1,144 @@
+// etb_runtime.cu -- runtime group of the C ABI (include/embtab_b200.h): HBM storage management
+// that replaces Julia `Array` storage for tables, plus error reporting.
+#include <stdarg.h>
+
+#include "etb_common.cuh"
+
+namespace etb {
+
+char* error_buffer() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+int32_t fail(int32_t status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+int32_t& launch_counter() {
+    static thread_local int32_t n = 0;
+    return n;
+}
+
+int32_t validate_table(const etb_table& t, const char* who) {
+    ETB_REQUIRE(elt_valid(t.elt), "%s: unsupported table element type %d", who, t.elt);
+    ETB_REQUIRE(t.dim > 0, "%s: table dim must be positive (got %d)", who, t.dim);
+    ETB_REQUIRE(t.ld >= t.dim, "%s: table ld (%d) < dim (%d)", who, t.ld, t.dim);
+    ETB_REQUIRE(t.nrows >= 0, "%s: negative nrows", who);
+    if (t.chunks) {
+        ETB_REQUIRE(t.shard_rows > 0 && t.shard_rows <= 0xffffffffll,
+                    "%s: split table needs 0 < shard_rows < 2^32 (got %lld)", who, (long long)t.shard_rows);
+    } else {
+        ETB_REQUIRE(t.base != nullptr || t.nrows == 0, "%s: table has neither base nor chunks", who);
+    }
+    return ETB_OK;
+}
+
+}  // namespace etb
+
+using namespace etb;
+
+extern "C" {
+
+int32_t etb_version(void) { return ETB_VERSION; }
+
+const char* etb_last_error(void) { return error_buffer(); }
+
+int32_t etb_last_launch_count(void) { return launch_counter(); }
+
+int32_t etb_device_count(int32_t* count_host) {
+    ETB_REQUIRE(count_host, "etb_device_count: null output");
+    int n = 0;
+    ETB_CUDA(cudaGetDeviceCount(&n));
+    *count_host = n;
+    return ETB_OK;
+}
+
+int32_t etb_init(int32_t device) {
+    ETB_CUDA(cudaSetDevice(device));
+    ETB_CUDA(cudaFree(0));
+    cudaDeviceProp prop;
+    ETB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ETB_ERR_UNSUPPORTED, "etb_init: device %d is sm_%d%d; this library is built for sm_100a only",
+                    device, prop.major, prop.minor);
+    return ETB_OK;
+}
+
+int32_t etb_malloc(void** ptr_host, size_t bytes) {
+    ETB_REQUIRE(ptr_host, "etb_malloc: null output");
+    *ptr_host = nullptr;
+    if (bytes == 0) return ETB_OK;
+    ETB_CUDA(cudaMalloc(ptr_host, bytes));
+    return ETB_OK;
+}
+
+int32_t etb_free(void* ptr) {
+    if (ptr) ETB_CUDA(cudaFree(ptr));
+    return ETB_OK;
+}
+
+int32_t etb_malloc_host(void** ptr_host, size_t bytes) {
+    ETB_REQUIRE(ptr_host, "etb_malloc_host: null output");
+    *ptr_host = nullptr;
+    if (bytes == 0) return ETB_OK;
+    ETB_CUDA(cudaMallocHost(ptr_host, bytes));
+    return ETB_OK;
+}
+
+int32_t etb_free_host(void* ptr_host) {
+    if (ptr_host) ETB_CUDA(cudaFreeHost(ptr_host));
+    return ETB_OK;
+}
+
+int32_t etb_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream) {
+    if (bytes == 0) return ETB_OK;
+    ETB_REQUIRE(dst && src_host, "etb_memcpy_h2d: null pointer");
+    ETB_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return ETB_OK;
+}
+
+int32_t etb_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return ETB_OK;
+    ETB_REQUIRE(dst_host && src, "etb_memcpy_d2h: null pointer");
+    ETB_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return ETB_OK;
+}
+
+int32_t etb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return ETB_OK;
+    ETB_REQUIRE(dst && src, "etb_memcpy_d2d: null pointer");
+    ETB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ETB_OK;
+}
+
+int32_t etb_memset(void* dst, int32_t byte, size_t bytes, void* stream) {
+    if (bytes == 0) return ETB_OK;
+    ETB_REQUIRE(dst, "etb_memset: null pointer");
+    ETB_CUDA(cudaMemsetAsync(dst, byte, bytes, (cudaStream_t)stream));
+    return ETB_OK;
+}
+
+int32_t etb_stream_create(void** stream_host) {
+    ETB_REQUIRE(stream_host, "etb_stream_create: null output");
+    cudaStream_t s;
+    ETB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream_host = (void*)s;
+    return ETB_OK;
+}
+
+int32_t etb_stream_sync(void* stream) {
+    ETB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return ETB_OK;
+}
+
+int32_t etb_stream_destroy(void* stream) {
+    if (stream) ETB_CUDA(cudaStreamDestroy((cudaStream_t)stream));
+    return ETB_OK;
+}
+
+}  // extern "C"

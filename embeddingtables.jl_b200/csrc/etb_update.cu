@@ -1,0 +1,600 @@
+// etb_update.cu -- K4 index! (sort + segment) and K5 fused segment-reduce + SGD (sm_100a).
+//
+// Replaces the reference's Indexer (histogram!/prefixsum!/remap!, src/utils.jl:370-553 -- a
+// stable counting sort of occurrence -> delta column by table row) and its update! kernels
+// (src/sparseupdate.jl:57-154, ensemble form :199-238).
+//
+// K4.  Every occurrence p of item t becomes the pair
+//          key = t << row_bits | (index - 1),      value = delta column of p (= p / bag)
+// All items are sorted at once by a stable LSD radix sort restricted to the bits the keys
+// actually use (cub::DeviceRadixSort -- library code, like cuBLAS would be for a GEMM), so
+// members of a bucket stay in occurrence order = the order remap! records (src/utils.jl:
+// 481-511).  Bucket starts are the positions whose key differs from the previous one,
+// compacted by cub::DeviceSelect.  Buckets come out in ascending (table, row) order instead
+// of the reference's first-seen order; buckets are disjoint table rows, so results do not
+// depend on that order.
+//
+// K5.  A group of G lanes owns one bucket: acc = 0; acc += delta[:, map[i]] for the bucket's
+// members in order (one lane per feature vector, like the lookup kernels, so the sum has the
+// reference's association, src/sparseupdate.jl:114-120); then one read-modify-write of the
+// table row with a fused multiply-add (muladd, src/sparseupdate.jl:123-127) or two roundings
+// (:88).  One bucket = one row = one writer: no atomics anywhere.
+#include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <vector>
+
+#include "etb_common.cuh"
+
+namespace etb {
+
+constexpr int kUThreads = 256;
+constexpr int kUMaxItems = 96;
+
+// ------------------------------------------------------------------------------------ layout
+struct IndexLayout {
+    int64_t n_total;
+    int32_t row_bits, slot_bits, key_bytes;
+    size_t off_keys[2], off_vals[2], off_offsets, off_nnz, off_temp, temp_bytes, total;
+};
+
+static int bits_for(uint64_t count) {  // bits needed to represent 0 .. count-1
+    int b = 0;
+    while (b < 63 && (1ull << b) < count) ++b;
+    return b;
+}
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct HeadPred32 {
+    const uint32_t* keys;
+    __device__ __forceinline__ bool operator()(int64_t p) const { return p == 0 || keys[p] != keys[p - 1]; }
+};
+struct HeadPred64 {
+    const uint64_t* keys;
+    __device__ __forceinline__ bool operator()(int64_t p) const { return p == 0 || keys[p] != keys[p - 1]; }
+};
+
+static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexLayout& L) {
+    ETB_REQUIRE(n_items >= 0, "etb_index: negative item count");
+    ETB_REQUIRE(n_items == 0 || items, "etb_index: null items");
+    int64_t n_total = 0, max_rows = 1;
+    for (int i = 0; i < n_items; ++i) {
+        const etb_update_item& it = items[i];
+        if (int32_t st = validate_table(it.table, "etb_index")) return st;
+        ETB_REQUIRE(idx_elt_valid(it.idx_elt), "etb_index: item %d: index type must be ETB_I32/ETB_I64", i);
+        ETB_REQUIRE(it.batch >= 0 && it.batch < 0x7fffffffll, "etb_index: item %d: bad batch %lld", i, (long long)it.batch);
+        ETB_REQUIRE(it.bag >= 0 && it.bag <= 0x7fffffffll, "etb_index: item %d: bad bag %lld", i, (long long)it.bag);
+        ETB_REQUIRE(it.bag == 0 || it.ld_idx >= it.bag, "etb_index: item %d: ld_idx < bag", i);
+        n_total += it.batch * (it.bag ? it.bag : 1);
+        max_rows = std::max(max_rows, it.table.nrows);
+    }
+    ETB_REQUIRE(n_total < 0x7fffffffll, "etb_index: %lld occurrences exceed the 2^31 limit of one call", (long long)n_total);
+    L.n_total = n_total;
+    L.row_bits = std::max(1, bits_for((uint64_t)max_rows));
+    L.slot_bits = bits_for((uint64_t)std::max(1, n_items));
+    ETB_REQUIRE(L.row_bits + L.slot_bits <= 64, "etb_index: key does not fit 64 bits");
+    L.key_bytes = (L.row_bits + L.slot_bits <= 32) ? 4 : 8;
+    const size_t n = (size_t)std::max<int64_t>(n_total, 1);
+    size_t off = 0;
+    for (int b = 0; b < 2; ++b) { L.off_keys[b] = off; off = align_up(off + n * L.key_bytes); }
+    for (int b = 0; b < 2; ++b) { L.off_vals[b] = off; off = align_up(off + n * sizeof(int32_t)); }
+    L.off_offsets = off; off = align_up(off + (n + 1) * sizeof(int64_t));
+    L.off_nnz = off; off = align_up(off + sizeof(int64_t));
+    // CUB temp storage: max over the sort and the select
+    size_t t_sort = 0, t_sel = 0;
+    const int end_bit = L.row_bits + L.slot_bits;
+    if (L.key_bytes == 4) {
+        cub::DoubleBuffer<uint32_t> k(nullptr, nullptr);
+        cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+        ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
+        ETB_CUDA(cub::DeviceSelect::If(nullptr, t_sel, thrust::counting_iterator<int64_t>(0), (int64_t*)nullptr,
+                                       (int64_t*)nullptr, (int64_t)n, HeadPred32{nullptr}));
+    } else {
+        cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
+        cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+        ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
+        ETB_CUDA(cub::DeviceSelect::If(nullptr, t_sel, thrust::counting_iterator<int64_t>(0), (int64_t*)nullptr,
+                                       (int64_t*)nullptr, (int64_t)n, HeadPred64{nullptr}));
+    }
+    L.off_temp = off;
+    L.temp_bytes = std::max(t_sort, t_sel);
+    L.total = align_up(off + L.temp_bytes);
+    return ETB_OK;
+}
+
+// ------------------------------------------------------------------------------------ K4a keys
+struct KeyDesc {
+    const void* idx;
+    int64_t start;   // first pair of this item in the concatenated arrays
+    uint32_t n;      // occurrences
+    uint32_t bag;    // 0 = vector
+    uint32_t ld_idx;
+    uint32_t pad;
+};
+struct KeyParams {
+    KeyDesc item[kUMaxItems];
+    int32_t row_bits;
+    int32_t slot0;  // slot number of item[0] (launches are chunked by kUMaxItems)
+};
+
+template <typename KeyT, typename IdxT>
+__global__ void __launch_bounds__(kUThreads)
+make_pairs_kernel(const __grid_constant__ KeyParams P, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
+    const KeyDesc& d = P.item[blockIdx.y];
+    const KeyT slot = (KeyT)(P.slot0 + blockIdx.y) << P.row_bits;
+    for (uint32_t p = blockIdx.x * kUThreads + threadIdx.x; p < d.n; p += gridDim.x * kUThreads) {
+        uint32_t col = p, pos = p;
+        if (d.bag) {  // flat column-major traversal (reference `columns`, src/utils.jl:312-320)
+            col = p / d.bag;
+            pos = col * d.ld_idx + (p - col * d.bag);
+        }
+        const int64_t i1 = (int64_t)__ldg((const IdxT*)d.idx + pos);
+        keys[d.start + p] = slot | (KeyT)(i1 - 1);
+        vals[d.start + p] = (int32_t)col;
+    }
+}
+
+// ------------------------------------------------------------------------------------ K5
+struct UpdDesc {  // 48 bytes
+    DevTable table;
+    const char* delta;
+    int64_t ld_delta_bytes;
+};
+struct UpdParams {
+    UpdDesc item[kUMaxItems];
+    const void* keys;
+    const int32_t* map;
+    const int64_t* offsets;
+    const int64_t* nnz;
+    int64_t n_total;
+    double eta;
+    int32_t row_bits;
+    int32_t slot0, nslots;  // this launch handles slots [slot0, slot0 + nslots)
+    int32_t G, nvec;
+    int32_t fma;
+    int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:564-572
+};
+
+template <typename T>
+__device__ __forceinline__ T sgd_epilogue(T row, T acc, T eta, bool fma);
+template <>
+__device__ __forceinline__ float sgd_epilogue<float>(float row, float acc, float eta, bool fma) {
+    // fma:   muladd(-eta, acc, row), one rounding (reference src/sparseupdate.jl:108,123-127)
+    // else:  row - eta*acc, two roundings (reference :88); intrinsics forbid contraction
+    return fma ? __fmaf_rn(-eta, acc, row) : __fsub_rn(row, __fmul_rn(eta, acc));
+}
+template <>
+__device__ __forceinline__ double sgd_epilogue<double>(double row, double acc, double eta, bool fma) {
+    return fma ? __fma_rn(-eta, acc, row) : __dsub_rn(row, __dmul_rn(eta, acc));
+}
+
+template <typename T, int VB, int VPL, typename KeyT>
+__global__ void __launch_bounds__(kUThreads)
+sgd_update_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+    using V = Vec<T, VB>;
+    const int G = P.G, nvec = P.nvec;
+    const int gl = threadIdx.x & (G - 1);
+    const int64_t nnz = *P.nnz;
+    const int64_t groups_total = (int64_t)gridDim.x * (kUThreads / G);
+    const KeyT row_mask = (KeyT)(((KeyT)1 << P.row_bits) - 1);
+    const T eta = (T)P.eta;  // convert(eltype(table), opt.eta), reference src/sparseupdate.jl:173
+    const bool fma = P.fma != 0;
+
+    int64_t s_begin = 0, s_end = nnz;
+    if (P.num_splits > 0) {  // cumulative has nnz+1 entries; split_size = cdiv(nnz+1, num_splits)
+        const int64_t split = nnz / P.num_splits + 1;
+        s_begin = (int64_t)(P.this_split - 1) * split;
+        s_end = min((int64_t)P.this_split * split, nnz);
+    }
+    for (int64_t s = s_begin + (int64_t)blockIdx.x * (kUThreads / G) + threadIdx.x / G; s < s_end; s += groups_total) {
+        const int64_t start = __ldg(P.offsets + s);
+        const int64_t stop = (s + 1 < nnz) ? __ldg(P.offsets + s + 1) : P.n_total;
+        const KeyT key = __ldg((const KeyT*)P.keys + start);
+        const int slot = (int)(key >> P.row_bits) - P.slot0;
+        if (slot < 0 || slot >= P.nslots) continue;  // bucket of another launch's class
+        const UpdDesc& d = P.item[slot];
+        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(key & row_mask) + 1));
+
+        for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
+            int vi[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
+            // the row's old value is independent of the deltas: fetch it first so its latency
+            // overlaps the accumulation
+            V old[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) ld_plain<VB>(&old[p], row + vi[p]);
+            V acc[VPL];  // accum = zero(Tiled), reference src/sparseupdate.jl:114
+#pragma unroll
+            for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
+            for (int64_t i0 = start; i0 < stop; i0 += G) {
+                const int m = (int)min((int64_t)G, stop - i0);
+                const char* mine = d.delta + (int64_t)__ldg(P.map + i0 + min(gl, m - 1)) * d.ld_delta_bytes;
+                for (int j0 = 0; j0 < m; j0 += U) {
+                    const char* r[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) r[u] = shfl_ptr(mine, min(j0 + u, m - 1), G);
+                    V v[U][VPL];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p)
+                            if (u == 0 || j0 + u < m) ld_row<VB>(&v[u][p], r[u] + vi[p]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (j0 + u < m)
+#pragma unroll
+                            for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[u][p].e[k];
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) {
+                if (pass0 + gl + p * G < nvec) {
+                    V out;
+#pragma unroll
+                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, fma);
+                    *(V*)(row + vi[p]) = out;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ host
+static int pick_vb_update(const etb_update_item& it) {
+    const size_t es = elt_bytes(it.table.elt);
+    const size_t rowbytes = (size_t)it.table.dim * es;
+    const size_t stride = (size_t)it.table.ld * es;
+    const size_t ldd = (size_t)it.ld_delta * es;
+    for (size_t vb : {(size_t)16, (size_t)8}) {
+        if (vb < es) continue;
+        if (rowbytes % vb == 0 && stride % vb == 0 && ldd % vb == 0 && ((uintptr_t)it.table.base % vb) == 0 &&
+            ((uintptr_t)it.delta % vb) == 0)
+            return (int)vb;
+    }
+    return es == 8 ? 8 : 4;
+}
+
+struct UpdClass {
+    int32_t elt, vb, vpl, G, nvec;
+    bool operator==(const UpdClass& o) const {
+        return elt == o.elt && vb == o.vb && vpl == o.vpl && G == o.G && nvec == o.nvec;
+    }
+};
+
+static UpdClass classify_update(const etb_update_item& it) {
+    UpdClass c;
+    c.elt = it.table.elt;
+    c.vb = pick_vb_update(it);
+    c.nvec = (int)((size_t)it.table.dim * elt_bytes(it.table.elt) / c.vb);
+    c.G = std::min(32, pow2ceil(c.nvec));
+    const int per_lane = (c.nvec + c.G - 1) / c.G;
+    c.vpl = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
+    return c;
+}
+
+template <typename T, int VB, typename KeyT>
+static void launch_update_vpl(int vpl, int grid, cudaStream_t s, const UpdParams& P) {
+    switch (vpl) {
+        case 1: sgd_update_kernel<T, VB, 1, KeyT><<<grid, kUThreads, 0, s>>>(P); break;
+        case 2: sgd_update_kernel<T, VB, 2, KeyT><<<grid, kUThreads, 0, s>>>(P); break;
+        default: sgd_update_kernel<T, VB, 4, KeyT><<<grid, kUThreads, 0, s>>>(P); break;
+    }
+}
+
+template <typename T, typename KeyT>
+static void launch_update_vb(const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+    if constexpr (sizeof(T) == 4) {
+        if (c.vb == 4) return launch_update_vpl<T, 4, KeyT>(c.vpl, grid, s, P);
+    }
+    if (c.vb == 8) return launch_update_vpl<T, 8, KeyT>(c.vpl, grid, s, P);
+    return launch_update_vpl<T, 16, KeyT>(c.vpl, grid, s, P);
+}
+
+static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int32_t n_items,
+                          etb_index_view* view, cudaStream_t stream) {
+    IndexLayout L;
+    if (int32_t st = make_layout(items, n_items, L)) return st;
+    ETB_REQUIRE(ws != nullptr, "etb_index: null workspace");
+    if (ws_bytes < L.total)
+        return fail(ETB_ERR_WORKSPACE, "etb_index: workspace has %zu bytes, needs %zu", ws_bytes, L.total);
+    char* base = (char*)ws;
+    int64_t* offsets = (int64_t*)(base + L.off_offsets);
+    int64_t* nnz = (int64_t*)(base + L.off_nnz);
+    int32_t* vals[2] = {(int32_t*)(base + L.off_vals[0]), (int32_t*)(base + L.off_vals[1])};
+    void* keys[2] = {base + L.off_keys[0], base + L.off_keys[1]};
+    const int end_bit = L.row_bits + L.slot_bits;
+
+    if (L.n_total == 0) {
+        ETB_CUDA(cudaMemsetAsync(nnz, 0, sizeof(int64_t), stream));
+    } else {
+        // K4a: (key, delta column) pairs of every item
+        static thread_local KeyParams KP;
+        int64_t start = 0;
+        for (int i0 = 0; i0 < n_items; i0 += kUMaxItems) {
+            const int n = std::min(kUMaxItems, n_items - i0);
+            uint32_t max_n = 0;
+            int idx_elt = items[i0].idx_elt;
+            bool uniform_idx = true;
+            for (int j = 0; j < n; ++j) {
+                const etb_update_item& it = items[i0 + j];
+                KeyDesc& d = KP.item[j];
+                d.idx = it.idx;
+                d.start = start;
+                d.n = (uint32_t)(it.batch * (it.bag ? it.bag : 1));
+                d.bag = (uint32_t)it.bag;
+                d.ld_idx = (uint32_t)it.ld_idx;
+                d.pad = 0;
+                start += d.n;
+                max_n = std::max(max_n, d.n);
+                uniform_idx = uniform_idx && it.idx_elt == idx_elt;
+                ETB_REQUIRE(d.n == 0 || it.idx, "etb_index: item %d: null indices", i0 + j);
+            }
+            ETB_REQUIRE(uniform_idx, "etb_index: all items of one call must share the index element type");
+            if (max_n == 0) continue;
+            KP.row_bits = L.row_bits;
+            KP.slot0 = i0;
+            dim3 grid(std::min<uint32_t>((max_n + kUThreads - 1) / kUThreads, 8u * kNumSMs), (unsigned)n);
+            if (L.key_bytes == 4) {
+                if (idx_elt == ETB_I64) make_pairs_kernel<uint32_t, long long><<<grid, kUThreads, 0, stream>>>(KP, (uint32_t*)keys[0], vals[0]);
+                else make_pairs_kernel<uint32_t, int><<<grid, kUThreads, 0, stream>>>(KP, (uint32_t*)keys[0], vals[0]);
+            } else {
+                if (idx_elt == ETB_I64) make_pairs_kernel<uint64_t, long long><<<grid, kUThreads, 0, stream>>>(KP, (uint64_t*)keys[0], vals[0]);
+                else make_pairs_kernel<uint64_t, int><<<grid, kUThreads, 0, stream>>>(KP, (uint64_t*)keys[0], vals[0]);
+            }
+            ETB_LAUNCHED();
+        }
+        // K4b: stable radix sort over the used key bits, then bucket heads
+        size_t temp_bytes = L.temp_bytes;
+        void* temp = base + L.off_temp;
+        cub::DoubleBuffer<int32_t> v(vals[0], vals[1]);
+        if (L.key_bytes == 4) {
+            cub::DoubleBuffer<uint32_t> k((uint32_t*)keys[0], (uint32_t*)keys[1]);
+            ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, L.n_total, 0, end_bit, stream));
+            keys[0] = k.Current();
+            temp_bytes = L.temp_bytes;
+            ETB_CUDA(cub::DeviceSelect::If(temp, temp_bytes, thrust::counting_iterator<int64_t>(0), offsets, nnz,
+                                           L.n_total, HeadPred32{(const uint32_t*)keys[0]}, stream));
+        } else {
+            cub::DoubleBuffer<uint64_t> k((uint64_t*)keys[0], (uint64_t*)keys[1]);
+            ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, L.n_total, 0, end_bit, stream));
+            keys[0] = k.Current();
+            temp_bytes = L.temp_bytes;
+            ETB_CUDA(cub::DeviceSelect::If(temp, temp_bytes, thrust::counting_iterator<int64_t>(0), offsets, nnz,
+                                           L.n_total, HeadPred64{(const uint64_t*)keys[0]}, stream));
+        }
+        vals[0] = v.Current();
+        // CUB launches: histogram + one pass per 8 key bits (onesweep), select = 2 kernels
+        launch_counter() += 1 + (end_bit + 7) / 8 + 2;
+    }
+    if (view) {
+        view->keys = keys[0];
+        view->map = vals[0];
+        view->offsets = offsets;
+        view->nnz = nnz;
+        view->n_total = L.n_total;
+        view->key_bytes = L.key_bytes;
+        view->row_bits = L.row_bits;
+        view->num_splits = 0;
+        view->this_split = 0;
+    }
+    return ETB_OK;
+}
+
+static int32_t update_impl(const etb_index_view* view, const etb_update_item* items, int32_t n_items, double eta,
+                           int32_t flags, cudaStream_t stream) {
+    ETB_REQUIRE(view, "etb_sgd_update: null index view");
+    ETB_REQUIRE(n_items >= 0 && (n_items == 0 || items), "etb_sgd_update: bad items");
+    if (n_items == 0 || view->n_total == 0) return ETB_OK;
+    std::vector<UpdClass> cls((size_t)n_items);
+    for (int i = 0; i < n_items; ++i) {
+        const etb_update_item& it = items[i];
+        if (int32_t st = validate_table(it.table, "etb_sgd_update")) return st;
+        // update! on integer tables throws in the reference too (InexactError at
+        // convert(eltype(table), opt.eta), src/sparseupdate.jl:173)
+        ETB_REQUIRE(it.table.elt == ETB_F32 || it.table.elt == ETB_F64,
+                    "etb_sgd_update: item %d: only Float32/Float64 tables can be updated", i);
+        ETB_REQUIRE(it.batch == 0 || it.delta, "etb_sgd_update: item %d: null delta", i);
+        ETB_REQUIRE(it.ld_delta >= it.table.dim, "etb_sgd_update: item %d: ld_delta < dim", i);
+        cls[i] = classify_update(it);
+    }
+    static thread_local UpdParams P;
+    P.keys = view->keys;
+    P.map = view->map;
+    P.offsets = view->offsets;
+    P.nnz = view->nnz;
+    P.n_total = view->n_total;
+    P.eta = eta;
+    P.row_bits = view->row_bits;
+    P.fma = (flags & ETB_UPDATE_FMA) ? 1 : 0;
+    ETB_REQUIRE(view->num_splits >= 0 && (view->num_splits == 0 || (view->this_split >= 1 && view->this_split <= view->num_splits)),
+                "etb_sgd_update: bad IndexerView split %d of %d", view->this_split, view->num_splits);
+    P.num_splits = view->num_splits;
+    P.this_split = view->this_split;
+    // one launch per run of consecutive items sharing a kernel class (all tables of a DLRM
+    // ensemble share it: one launch)
+    for (int i0 = 0; i0 < n_items;) {
+        const UpdClass c = cls[i0];
+        int n = 0;
+        while (i0 + n < n_items && n < kUMaxItems && cls[i0 + n] == c) {
+            const etb_update_item& it = items[i0 + n];
+            UpdDesc& d = P.item[n];
+            d.table = make_dev_table(it.table);
+            d.delta = (const char*)it.delta;
+            d.ld_delta_bytes = it.ld_delta * (int64_t)elt_bytes(it.table.elt);
+            ++n;
+        }
+        P.slot0 = i0;
+        P.nslots = n;
+        P.G = c.G;
+        P.nvec = c.nvec;
+        const int64_t groups_per_block = kUThreads / c.G;
+        const int64_t want = (view->n_total + groups_per_block - 1) / groups_per_block;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8);  // persistent, grid-stride over buckets
+        if (view->key_bytes == 4) {
+            if (c.elt == ETB_F32) launch_update_vb<float, uint32_t>(c, grid, stream, P);
+            else launch_update_vb<double, uint32_t>(c, grid, stream, P);
+        } else {
+            if (c.elt == ETB_F32) launch_update_vb<float, uint64_t>(c, grid, stream, P);
+            else launch_update_vb<double, uint64_t>(c, grid, stream, P);
+        }
+        ETB_LAUNCHED();
+        i0 += n;
+    }
+    return ETB_OK;
+}
+
+// ------------------------------------------------------------------------------------ uncompress
+template <typename T, typename IdxT>
+__global__ void uncompress_kernel(T* dst, int64_t ld_dst, int dim, const T* delta, int64_t ld_delta, const IdxT* idx,
+                                  int64_t bag, int64_t batch, int64_t ld_idx) {
+    // one thread per feature element walks every occurrence in order: deterministic, and the
+    // same association as the reference's `columnview(dst, c) .+= update` loop
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= dim) return;
+    const int64_t per = bag ? bag : 1;
+    for (int64_t j = 0; j < batch; ++j) {
+        const T g = delta[j * ld_delta + k];
+        for (int64_t i = 0; i < per; ++i) {
+            const int64_t c = (int64_t)(bag ? idx[j * ld_idx + i] : idx[j]);
+            dst[(c - 1) * ld_dst + k] += g;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ a2a pack / unpack
+struct A2ABlocks {
+    int64_t rows[16];
+    int64_t row_off[16];
+    int64_t buf_off[16];  // element offset of block r in the dense buffer
+};
+
+template <int VB, bool UNPACK>
+__global__ void __launch_bounds__(256)
+a2a_copy_kernel(char* strided, int64_t ld_bytes, char* dense, const __grid_constant__ A2ABlocks B, int64_t batch_local,
+                int es) {
+    const int r = blockIdx.y;
+    const int64_t row_bytes = B.rows[r] * es;
+    const int64_t vec_per_col = row_bytes / VB;
+    const int64_t total = vec_per_col * batch_local;
+    char* dbase = dense + B.buf_off[r] * es;
+    char* sbase = strided + B.row_off[r] * es;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t col = t / vec_per_col, v = t - col * vec_per_col;
+        char* s = sbase + col * ld_bytes + v * VB;
+        char* d = dbase + col * row_bytes + v * VB;
+        Vec<uint32_t, VB> x;
+        if (UNPACK) { ld_row<VB>(&x, d); st_stream<VB>(s, &x); }
+        else { ld_row<VB>(&x, s); st_stream<VB>(d, &x); }
+    }
+}
+
+static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, const int64_t* rows, const int64_t* row_off,
+                        int32_t nranks, int64_t batch_local, int32_t elt, cudaStream_t stream) {
+    launch_counter() = 0;
+    ETB_REQUIRE(nranks >= 1 && nranks <= 16, "etb_a2a: nranks must be in 1..16");
+    ETB_REQUIRE(elt_valid(elt), "etb_a2a: bad element type");
+    ETB_REQUIRE(strided && dense && rows && row_off, "etb_a2a: null pointer");
+    if (batch_local == 0) return ETB_OK;
+    const int es = (int)elt_bytes(elt);
+    A2ABlocks B;
+    int64_t off = 0, max_rows = 0;
+    int vb = 16;
+    for (int r = 0; r < nranks; ++r) {
+        B.rows[r] = rows[r];
+        B.row_off[r] = row_off[r];
+        B.buf_off[r] = off;
+        off += rows[r] * batch_local;
+        max_rows = std::max(max_rows, rows[r]);
+        while (vb > es && ((rows[r] * es) % vb || (row_off[r] * es) % vb || (B.buf_off[r] * es) % vb)) vb >>= 1;
+    }
+    while (vb > es && ((ld * es) % vb || (uintptr_t)strided % vb || (uintptr_t)dense % vb)) vb >>= 1;
+    if (vb < 4) vb = 4;
+    if (max_rows == 0) return ETB_OK;
+    const int64_t total = max_rows * es / vb * batch_local;
+    dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8), (unsigned)nranks);
+    const int64_t ldb = ld * es;
+#define ETB_A2A(VBV)                                                                                          \
+    if (unpack) a2a_copy_kernel<VBV, true><<<grid, 256, 0, stream>>>((char*)strided, ldb, (char*)dense, B, batch_local, es); \
+    else a2a_copy_kernel<VBV, false><<<grid, 256, 0, stream>>>((char*)strided, ldb, (char*)dense, B, batch_local, es);
+    if (vb == 16) { ETB_A2A(16) } else if (vb == 8) { ETB_A2A(8) } else { ETB_A2A(4) }
+#undef ETB_A2A
+    ETB_LAUNCHED();
+    return ETB_OK;
+}
+
+}  // namespace etb
+
+using namespace etb;
+
+extern "C" {
+
+int32_t etb_index_workspace_bytes(const etb_update_item* items_host, int32_t n_items, size_t* bytes_host) {
+    ETB_REQUIRE(bytes_host, "etb_index_workspace_bytes: null output");
+    IndexLayout L;
+    if (int32_t st = make_layout(items_host, n_items, L)) return st;
+    *bytes_host = L.total;
+    return ETB_OK;
+}
+
+int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item* items_host, int32_t n_items,
+                  etb_index_view* view_host, void* stream) {
+    launch_counter() = 0;
+    return index_impl(workspace, workspace_bytes, items_host, n_items, view_host, (cudaStream_t)stream);
+}
+
+int32_t etb_sgd_update(const etb_index_view* view_host, const etb_update_item* items_host, int32_t n_items, double eta,
+                       int32_t flags, void* stream) {
+    launch_counter() = 0;
+    return update_impl(view_host, items_host, n_items, eta, flags, (cudaStream_t)stream);
+}
+
+int32_t etb_index_and_update(void* workspace, size_t workspace_bytes, const etb_update_item* items_host,
+                             int32_t n_items, double eta, int32_t flags, void* stream) {
+    launch_counter() = 0;
+    etb_index_view view;
+    if (int32_t st = index_impl(workspace, workspace_bytes, items_host, n_items, &view, (cudaStream_t)stream)) return st;
+    return update_impl(&view, items_host, n_items, eta, flags, (cudaStream_t)stream);
+}
+
+int32_t etb_uncompress(void* dst, int64_t ld_dst, int32_t dim, int32_t elt, const void* delta, int64_t ld_delta,
+                       const void* idx, int32_t idx_elt, int64_t bag, int64_t batch, int64_t ld_idx, void* stream) {
+    launch_counter() = 0;
+    ETB_REQUIRE(elt == ETB_F32 || elt == ETB_F64, "etb_uncompress: only Float32/Float64");
+    ETB_REQUIRE(idx_elt_valid(idx_elt), "etb_uncompress: bad index type");
+    ETB_REQUIRE(dim > 0 && batch >= 0 && bag >= 0, "etb_uncompress: bad sizes");
+    if (batch == 0) return ETB_OK;
+    ETB_REQUIRE(dst && delta && idx, "etb_uncompress: null pointer");
+    const int threads = 128, blocks = (dim + threads - 1) / threads;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (elt == ETB_F32) {
+        if (idx_elt == ETB_I64) uncompress_kernel<float, long long><<<blocks, threads, 0, s>>>((float*)dst, ld_dst, dim, (const float*)delta, ld_delta, (const long long*)idx, bag, batch, ld_idx);
+        else uncompress_kernel<float, int><<<blocks, threads, 0, s>>>((float*)dst, ld_dst, dim, (const float*)delta, ld_delta, (const int*)idx, bag, batch, ld_idx);
+    } else {
+        if (idx_elt == ETB_I64) uncompress_kernel<double, long long><<<blocks, threads, 0, s>>>((double*)dst, ld_dst, dim, (const double*)delta, ld_delta, (const long long*)idx, bag, batch, ld_idx);
+        else uncompress_kernel<double, int><<<blocks, threads, 0, s>>>((double*)dst, ld_dst, dim, (const double*)delta, ld_delta, (const int*)idx, bag, batch, ld_idx);
+    }
+    ETB_LAUNCHED();
+    return ETB_OK;
+}
+
+int32_t etb_a2a_unpack(void* dst, int64_t ld_dst, const void* recv, const int64_t* rows_host, const int64_t* row_off_host,
+                       int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
+    return a2a_copy(true, dst, ld_dst, const_cast<void*>(recv), rows_host, row_off_host, nranks, batch_local, elt,
+                    (cudaStream_t)stream);
+}
+
+int32_t etb_a2a_pack(void* send, const void* src, int64_t ld_src, const int64_t* rows_host, const int64_t* row_off_host,
+                     int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
+    return a2a_copy(false, const_cast<void*>(src), ld_src, send, rows_host, row_off_host, nranks, batch_local, elt,
+                    (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -40,6 +40,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 #define ETB_VERSION 100 /* 0.1.0 */
 
@@ -177,17 +180,15 @@ int32_t etb_last_launch_count(void);
  * (reference src/sparseupdate.jl:211-213).  Buckets come out in ascending (table, row) order
  * instead of first-seen order; bucket members keep the reference's order.
  *
- * Workspace contents after the call (see etb_index_view):
- *   keys[N]      sorted composite keys (table_slot << rowbits | row-1), uint32 or uint64
- *   map[N]       delta column (0-based) of each sorted position        (reference `map`)
- *   offsets[nnz] start of each bucket in keys/map                      (reference `cumulative`)
- *   nnz          number of buckets (device int64; offsets[nnz] is not stored, it equals N)
+ * The result is described by an etb_index_view (a host POD of device pointers into the
+ * caller's workspace -- the GPU analogue of the Indexer's `cumulative` and `map` fields,
+ * reference src/utils.jl:527-532):
+ *   keys[n_total]  sorted composite keys (table_slot << row_bits | row-1), uint32 or uint64
+ *   map[n_total]   delta column (0-based) of each sorted position        (reference `map`)
+ *   offsets[nnz]   start of each bucket in keys/map                      (reference `cumulative`)
+ *   nnz            number of buckets (device int64; bucket s ends at offsets[s+1], or at
+ *                  n_total for the last one)
  */
-int32_t etb_index_workspace_bytes(const etb_update_item* items_host, int32_t n_items,
-                                  size_t* bytes_host);
-int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item* items_host,
-                  int32_t n_items, void* stream);
-
 typedef struct etb_index_view {
     const void* keys;       /* device */
     const int32_t* map;     /* device */
@@ -196,17 +197,27 @@ typedef struct etb_index_view {
     int64_t n_total;        /* sum of occurrences over items */
     int32_t key_bytes;      /* 4 or 8 */
     int32_t row_bits;       /* key = slot << row_bits | (row-1) */
+    /* IndexerView(indexer, num_splits, this_split), reference src/utils.jl:559-577: restrict an
+     * update to buckets (this_split-1)*s .. min(this_split*s, nnz)-1 with s = cdiv(nnz+1,
+     * num_splits).  num_splits == 0 (what etb_index writes) = all buckets. */
+    int32_t num_splits;
+    int32_t this_split;     /* 1-based */
 } etb_index_view;
-int32_t etb_index_get_view(const void* workspace, etb_index_view* view_host);
+
+int32_t etb_index_workspace_bytes(const etb_update_item* items_host, int32_t n_items,
+                                  size_t* bytes_host);
+int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item* items_host,
+                  int32_t n_items, etb_index_view* view_host, void* stream);
 
 /* ---------------------------------------------------------------- update! ------------- */
 /* K5. For every bucket (distinct row k of table t): acc = 0; acc += delta_t[:, col] for the
  * bucket's members in order; A_t[:, k] = fma(-eta, acc, A_t[:, k]) (ETB_UPDATE_FMA) or
  * A_t[:, k] - eta*acc.  No atomics: one bucket = one table row = one writer.
  * Replaces update!(table, update, indexer, alpha) reference src/sparseupdate.jl:57-154 and the
- * ensemble form :199-238.  `workspace` must hold the result of etb_index on the SAME items. */
-int32_t etb_sgd_update(const void* workspace, const etb_update_item* items_host, int32_t n_items,
-                       double eta, int32_t flags, void* stream);
+ * ensemble form :199-238.  `view_host` must be the result of etb_index on the SAME items.
+ * eta is converted to the table's element type (reference src/sparseupdate.jl:173). */
+int32_t etb_sgd_update(const etb_index_view* view_host, const etb_update_item* items_host,
+                       int32_t n_items, double eta, int32_t flags, void* stream);
 
 /* update!(opt, table(s), grad(s)): etb_index followed by etb_sgd_update
  * (reference src/sparseupdate.jl:160-178). */
@@ -216,10 +227,10 @@ int32_t etb_index_and_update(void* workspace, size_t workspace_bytes,
 
 /* Debug/test helper: dense gradient of a SparseEmbeddingUpdate.
  * dst (dim x ncols, ld_dst) must be zeroed by the caller; accumulates in occurrence order.
- * Replaces uncompress(), reference src/sparseupdate.jl:16-32. */
-int32_t etb_uncompress(void* dst, int64_t ld_dst, int64_t ncols, int32_t dim, int32_t elt,
-                       const void* delta, int64_t ld_delta, const void* idx, int32_t idx_elt,
-                       int64_t bag, int64_t batch, int64_t ld_idx, void* stream);
+ * Replaces uncompress(), reference src/sparseupdate.jl:16-32.  f32 / f64 only. */
+int32_t etb_uncompress(void* dst, int64_t ld_dst, int32_t dim, int32_t elt, const void* delta,
+                       int64_t ld_delta, const void* idx, int32_t idx_elt, int64_t bag,
+                       int64_t batch, int64_t ld_idx, void* stream);
 
 /* ---------------------------------------------------------------- multi-GPU ----------- */
 /* Table-wise sharded ensembles exchange pooled outputs / cotangents between ranks.  The
@@ -237,6 +248,9 @@ int32_t etb_a2a_pack(void* send, const void* src, int64_t ld_src, const int64_t*
                      const int64_t* row_off_host, int32_t nranks, int64_t batch_local, int32_t elt,
                      void* stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

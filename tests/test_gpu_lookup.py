@@ -1,0 +1,248 @@
+"""GPU parity: lookup / lookup! / maplookup -- the reference's test/lookup.jl, test/map.jl and
+test/constructors.jl re-expressed against the C-ABI library, with the CPU oracle as checker.
+Bit-exact (`==`) everywhere: gathers are bit copies and pooled sums keep the reference's
+left-to-right association."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def E():
+    import embtab
+    return embtab
+
+
+@pytest.fixture(scope="module")
+def O():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+NROWS = [32, 64, 128, 256, 512, 1024, 1504]  # reference test/lookup.jl:67
+NCOLS = 1000
+
+
+def make_tables(E, O, base, kind, shard=None):
+    if kind == "dynamic":
+        return E.SimpleEmbedding(base), O.Table(base, static=False)
+    if kind == "static":
+        return E.SimpleEmbedding(base, E.Static(base.shape[0])), O.Table(base, static=True)
+    return E.SplitEmbedding(base, shard), O.Table(base, cols_per_shard=shard)
+
+
+def test_readme_examples(E, golden):
+    g = golden["readme_lookup"]
+    A = E.SimpleEmbedding(np.array(g["data_rows"], np.int64))
+    assert E.lookup(A, g["gather"]["inds"]).numpy().tolist() == g["gather"]["expect_rows"]
+    assert E.lookup(A, np.array(g["pooled"]["inds_rows"])).numpy().tolist() == g["pooled"]["expect_rows"]
+    g = golden["readme_maplookup"]
+    tables = [E.SimpleEmbedding(np.array(g["A_rows"], np.int64)), E.SimpleEmbedding(np.array(g["B_rows"], np.int64))]
+    res = E.maplookup(tables, [g["iA"], g["iB"]])
+    assert res[0].numpy().tolist() == g["expect_A_rows"] and res[1].numpy().tolist() == g["expect_B_rows"]
+    res2 = E.maplookup(tables, np.stack([g["iA"], g["iB"]], axis=1))
+    assert all(np.array_equal(a.numpy(), b.numpy()) for a, b in zip(res, res2))
+
+
+def test_constructors(E, golden):
+    # reference test/constructors.jl:1-25
+    even, odd = np.random.rand(64, 10).astype(np.float32), np.random.rand(65, 10).astype(np.float32)
+    x = E.SimpleEmbedding(even, E.Static(64))
+    assert x.size() == even.shape
+    with pytest.raises(E.ArgumentError):
+        E.SimpleEmbedding(even, E.Static(32))
+    with pytest.raises(E.ArgumentError):
+        E.SimpleEmbedding(even, E.Static(64.0))
+    x = E.SimpleEmbedding(odd)
+    assert x.size() == odd.shape and isinstance(x.lookup_type, E.Dynamic)
+    x = E.SimpleEmbedding(odd, E.Static(65))
+    assert x.size() == odd.shape and x.lookup_type == E.Static(65)
+
+
+def test_custom_table_type(E, O):
+    # reference test/constructors.jl:34-54: a user-defined table implementing only the contract
+    class DummyEmbedding(E.AbstractEmbeddingTable):
+        def __init__(self, data):
+            self.data = E.DeviceArray.from_numpy(data)
+            self.lookup_type, self.dtype = E.Dynamic(), self.data.dtype
+
+        def size(self, d=None):
+            return self.data.size(d)
+
+        def columnpointer(self, i, ctx=None):
+            return E.columnpointer(self.data, i)
+
+        def example(self):
+            return self.data
+
+        def descriptor(self):
+            d = self.data
+            from embtab import _lib
+            return _lib.Table(d.ptr, None, d.shape[1], 0, d.shape[0], d.ld, d.elt, 0)
+
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((10, 10)).astype(np.float32)
+    table = DummyEmbedding(base)
+    inds = rng.integers(1, 11, (10, 10))
+    assert np.array_equal(E.lookup(table, inds).numpy(), O.lookup(O.Table(base), inds))
+
+
+@pytest.mark.parametrize("rows", NROWS)
+@pytest.mark.parametrize("kind", ["dynamic", "static"])
+def test_simple_lookup(E, O, rows, kind):
+    rng = np.random.default_rng(rows)
+    base = rng.random((rows, NCOLS), dtype=np.float32)
+    table, ref = make_tables(E, O, base, kind)
+    assert table == base and len(table) == base.size          # `table == baseline`, test/lookup.jl:78
+    for _ in range(3):
+        I = rng.permutation(NCOLS) + 1                         # no repeats, test/lookup.jl:14-20
+        assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+        I = rng.integers(1, NCOLS + 1, NCOLS)                  # repeats, :23-29
+        assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+        I = np.stack([rng.permutation(NCOLS - 1) + 2 for _ in range(12)])  # bag 12, batch 999, :42-48
+        assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+        I = rng.integers(1, NCOLS + 1, (12, NCOLS))            # :51-56
+        assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+
+
+@pytest.mark.parametrize("rows", NROWS)
+@pytest.mark.parametrize("shard", [10, 30, 50])
+def test_split_lookup(E, O, rows, shard):
+    # reference test/lookup.jl:110-138 (ragged last chunk for 30)
+    rng = np.random.default_rng(rows + shard)
+    base = rng.random((rows, NCOLS), dtype=np.float32)
+    table, ref = make_tables(E, O, base, "split", shard)
+    assert table == base
+    I = rng.integers(1, NCOLS + 1, NCOLS)
+    assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+    I = rng.integers(1, NCOLS + 1, (12, NCOLS))
+    assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
+@pytest.mark.parametrize("dim", [1, 3, 5, 6, 16, 20, 33, 80, 100, 130])
+def test_odd_dims_and_dtypes(E, O, dim, dtype):
+    # feature sizes that force the 8- and 4-byte vector paths and partially filled groups;
+    # integer tables must be bit-exact (wrapping adds)
+    rng = np.random.default_rng(dim)
+    if np.issubdtype(dtype, np.integer):
+        info = np.iinfo(dtype)
+        base = rng.integers(info.min, info.max, (dim, 300), dtype=dtype)
+    else:
+        base = (rng.standard_normal((dim, 300)) * 1e3).astype(dtype)
+    table, ref = E.SimpleEmbedding(base), O.Table(base)
+    for bag in (1, 2, 7, 32, 33, 70):
+        I = rng.integers(1, 301, (bag, 257))
+        assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I)), (dim, dtype, bag)
+    I = rng.integers(1, 301, 1001)
+    assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(ref, I))
+
+
+def test_int32_indices_and_negative_zero(E, O):
+    rng = np.random.default_rng(1)
+    base = rng.standard_normal((64, 50)).astype(np.float32)
+    base[:, 0] = -0.0   # a bag of only -0.0 rows must give -0.0 (accumulator seeded with row 1)
+    base[:, 1] = 0.0
+    table, ref = E.SimpleEmbedding(base, E.Static(64)), O.Table(base, static=True)
+    I = rng.integers(1, 51, (9, 40))
+    I[:, 0] = 1
+    I[:, 1] = [1, 2, 1, 2, 1, 2, 1, 2, 1]
+    got32 = E.lookup(table, I.astype(np.int32)).numpy()
+    got64 = E.lookup(table, I).numpy()
+    want = O.lookup(ref, I)
+    assert np.array_equal(got32.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(got64.view(np.uint32), want.view(np.uint32))
+    assert np.all(np.signbit(got64[:, 0])) and not np.any(np.signbit(got64[:, 1]))
+
+
+def test_empty_and_single(E, O):
+    base = np.arange(40, dtype=np.float32).reshape(8, 5, order="F")
+    table = E.SimpleEmbedding(base)
+    assert E.lookup(table, np.zeros(0, np.int64)).shape == (8, 0)
+    assert E.lookup(table, np.zeros((3, 0), np.int64)).shape == (8, 0)
+    assert np.array_equal(E.lookup(table, [5]).numpy(), base[:, 4:5])
+    assert np.array_equal(E.lookup(table, np.array([[5], [1]])).numpy(), base[:, 4:5] + base[:, 0:1])
+
+
+def test_lookup_inplace_strided_destination(E, O):
+    # lookup!(view(dst, rows, :), ...) -- what the PreallocationStrategy does per table
+    rng = np.random.default_rng(2)
+    base = rng.standard_normal((32, 100)).astype(np.float32)
+    table = E.SimpleEmbedding(base, E.Static(32))
+    big = E.DeviceArray.from_numpy(np.full((100, 64), 7.0, np.float32))
+    I = rng.integers(1, 101, (5, 64))
+    E.lookup_(big.rows(10, 42), table, I)
+    got = big.numpy()
+    assert np.array_equal(got[10:42], O.lookup(O.Table(base, static=True), I))
+    assert np.all(got[:10] == 7.0) and np.all(got[42:] == 7.0)
+
+
+# ---------------------------------------------------------------------------- maplookup
+def strategies(E):
+    return [E.DefaultStrategy(), E.SimpleParallelStrategy(), E.PreallocationStrategy()]
+
+
+@pytest.mark.parametrize("nrows", [16, 64, 512])
+@pytest.mark.parametrize("form", ["vecvec", "matrix", "vecmat", "3d"])
+def test_maplookup_forms(E, O, nrows, form):
+    # reference test/map.jl:14-100
+    rng = np.random.default_rng(nrows)
+    ncols, ntables, nlookups, batch = 100, 10, 10, 64
+    for rep in range(3):
+        base = [rng.standard_normal((nrows, ncols)).astype(np.float32) for _ in range(ntables)]
+        tables = [E.SimpleEmbedding(b, E.Static(nrows)) for b in base]
+        refs = [O.Table(b, static=True) for b in base]
+        if form == "vecvec":
+            inds = [rng.integers(1, ncols + 1, batch) for _ in range(ntables)]
+        elif form == "matrix":
+            inds = rng.integers(1, ncols + 1, (batch, ntables))
+        elif form == "vecmat":
+            inds = [rng.integers(1, ncols + 1, (nlookups, batch)) for _ in range(ntables)]
+        else:
+            inds = rng.integers(1, ncols + 1, (nlookups, batch, ntables))
+        reference = np.concatenate([O.lookup(r, i) for r, i in zip(refs, O.colwrap(refs, inds))], axis=0)
+        for s in strategies(E):
+            out = E.maplookup(s, tables, inds)
+            got = out.numpy() if isinstance(s, E.PreallocationStrategy) else np.concatenate([o.numpy() for o in out], axis=0)
+            assert np.array_equal(got, reference), (form, type(s).__name__)
+    out = E.maplookup(tables, inds)  # default strategy when omitted
+    assert np.array_equal(np.concatenate([o.numpy() for o in out], axis=0), reference)
+
+
+def test_preallocation_prependrows_untouched(E, O):
+    rng = np.random.default_rng(9)
+    dims = [16, 64, 5, 128]  # mixed feature sizes -> several kernel classes in one call
+    base = [rng.standard_normal((d, 77)).astype(np.float32) for d in dims]
+    tables = [E.SimpleEmbedding(b) for b in base]
+    inds = [rng.integers(1, 78, (4, 50)) for _ in dims]
+    ref = np.concatenate([O.lookup(O.Table(b), i) for b, i in zip(base, inds)], axis=0)
+    for prepend in (0, 20, 3):
+        dst = E.DeviceArray.from_numpy(np.full((prepend + sum(dims), 50), -3.0, np.float32))
+        out = E.maplookup_(E.PreallocationStrategy(prepend), dst, tables, inds)
+        assert out is dst
+        got = dst.numpy()
+        assert np.all(got[:prepend] == -3.0)          # reference src/lookup.jl:311-313: rows left alone
+        assert np.array_equal(got[prepend:], ref)
+    out = E.maplookup(E.PreallocationStrategy(20), tables, inds)
+    assert out.shape == (20 + sum(dims), 50) and np.array_equal(out.numpy()[20:], ref)
+
+
+def test_maplookup_split_tables_many(E, O):
+    # more tables than one launch holds (kMaxItems = 96), split storage, ragged chunks
+    rng = np.random.default_rng(4)
+    base = [rng.standard_normal((32, 64)).astype(np.float32) for _ in range(100)]
+    tables = [E.SplitEmbedding(b, 24) for b in base]
+    inds = rng.integers(1, 65, (3, 40, 100))
+    out = E.maplookup(E.PreallocationStrategy(), tables, inds).numpy()
+    ref = np.concatenate([O.lookup(O.Table(b, cols_per_shard=24), inds[:, :, t]) for t, b in enumerate(base)], axis=0)
+    assert np.array_equal(out, ref)
+
+
+def test_missing_library_fails_loudly(E, monkeypatch):
+    from embtab import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libembtab_b200.so")
+    with pytest.raises(E.EmbTabError):
+        E.lookup(E.SimpleEmbedding(np.zeros((4, 4), np.float32)), [1])
