@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline workload on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dist uniform|zipf]
+
+Workload (BASELINE.json configs[1], "C2"): DLRM-style pooled lookup, 26 tables x 1M rows x dim
+128 Float32, bag 32, batch 16384, PreallocationStrategy(prependrows=128).  One STEP = the whole
+hot path once over one batch: fused multi-table pooled lookup into the concatenated feature matrix
+(forward), the lazy pullback (SparseEmbeddingUpdate views of the cotangent), and the ensemble
+update!(Descent) (index! + fused segment-reduce + SGD).  metric = embedding lookups per second
+(lookups per step / step time); fwd+bwd+SGD GB/s is reported beside it.
+
+`value`    : tables, indices and cotangent already resident in HBM.
+`e2e`      : the same step through the public host API with HOST buffers: indices and cotangent
+             are copied in from pinned memory and the feature matrix is copied out, every step.
+`roofline` : the dominant kernel's algorithmic bytes / its CUDA-event duration, vs the measured
+             HBM copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` / --impl reference: the CPU oracle (a C port of the reference's algorithm --
+             the reference is Julia, which this image cannot run) on the box's host cores with
+             the reference's threaded strategies, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "embeddingtables.jl_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOAD = "C2: 26 tables x 1M rows x dim 128 f32, bag 32, batch 16384, PreallocationStrategy(prependrows=128): fwd + pullback + ensemble update!(Descent)"
+NT, NROWS, DIM, BAG, BATCH, PREPEND = 26, 1_000_000, 128, 32, 16384, 128
+ETA = 0.01
+SEED = 0xE7AB1E + 2
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def make_indices(rng, dist, nt, nrows, bag, batch):
+    """(bag, batch, nt) 1-based int64 indices, Julia 3-d container form."""
+    if dist == "uniform":
+        return rng.integers(1, nrows + 1, (bag, batch, nt), dtype=np.int64)
+    # Zipf(alpha=1.05) on 1..nrows by inverse CDF; rank -> row through a seeded permutation per table
+    w = 1.0 / np.arange(1, nrows + 1, dtype=np.float64) ** 1.05
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    out = np.empty((bag, batch, nt), dtype=np.int64, order="F")
+    for t in range(nt):
+        ranks = np.searchsorted(cdf, rng.random(bag * batch))
+        perm = rng.permutation(nrows)
+        out[:, :, t] = (perm[ranks] + 1).reshape(bag, batch, order="F")
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc = device, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        if sm:
+            self.result = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                           "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------- CPU arm
+def cpu_reference_arm(steps, warmup, dist, sample_tables=4):
+    """The reference's CPU path (C port = oracle/) on this box's host cores: PreallocationStrategy
+    forward (8 batch chunks x tables behind an atomic counter) + ensemble update! (index! per table,
+    then 4 bucket splits x tables behind an atomic counter), all host threads.  Bounded sample:
+    `sample_tables` of the 26 tables at the full batch/bag/dim (cost is linear in tables)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(SEED)
+    nt = sample_tables
+    tables = []
+    for _ in range(nt):
+        a = np.empty((DIM, NROWS), np.float32, order="F")
+        a.reshape(-1, order="F")[:] = rng.random(DIM * NROWS, dtype=np.float32)
+        tables.append(O.Table(a, static=True))
+    I = make_indices(rng, dist, nt, NROWS, BAG, BATCH)
+    Is = [np.asfortranarray(I[:, :, t]) for t in range(nt)]
+    out = np.zeros((PREPEND + nt * DIM, BATCH), np.float32, order="F")
+    delta = np.asfortranarray(rng.standard_normal(out.shape, dtype=np.float32))
+    deltas = [delta[PREPEND + DIM * k: PREPEND + DIM * (k + 1)] for k in range(nt)]
+    scratch = O.alloc_indexers(Is)  # caller-owned Indexers, reused like the reference's
+    lookups = nt * BATCH * BAG
+    t_fwd, t_upd = [], []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.maplookup("preallocation", tables, Is, prependrows=PREPEND, nthreads=cores, out=out)
+        t1 = time.perf_counter()
+        O.update_ensemble(tables, deltas, Is, ETA, num_splits=4, nthreads=cores, scratch=scratch)
+        t2 = time.perf_counter()
+        if s >= warmup:
+            t_fwd.append(t1 - t0); t_upd.append(t2 - t1)
+    step_s = float(np.mean(t_fwd) + np.mean(t_upd))
+    return {"value": lookups / step_s, "unit": "lookups/s", "cores": cores, "kind": "port",
+            "sample": f"{nt} of {NT} tables (1M x 128 f32), full batch {BATCH}, bag {BAG}, {dist} indices; "
+                      f"{steps} timed steps after {warmup} warm-up; C port of the reference (Julia absent), "
+                      f"AVX-512={bool(O.lib().etbo_uses_avx512())}",
+            "ms_per_step": step_s * 1e3, "fwd_ms": float(np.mean(t_fwd)) * 1e3, "update_ms": float(np.mean(t_upd)) * 1e3,
+            "lookups_per_step": lookups}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    r = cpu_reference_arm(steps, warmup, args.dist)
+    line = {"impl": "reference", "metric": "embedding_lookups_per_sec", "value": r["value"], "unit": "lookups/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "dist": args.dist, "note": "bounded sample; lookups/s is per-table linear"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"], "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import embtab as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    E._lib.check(E.lib().etb_init(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        from embtab import dist as ED  # table-wise sharded ensemble with all-to-all
+        return ED.bench_sharded(args, rank, world, local, globals())
+
+    lib = E.lib()
+    rng = np.random.default_rng(SEED)
+    # ---- synthetic state, resident in HBM ------------------------------------------------
+    gen = torch.Generator(device="cuda").manual_seed(SEED)
+    tables = []
+    for _ in range(NT):
+        buf = torch.rand(DIM * NROWS, device="cuda", dtype=torch.float32, generator=gen)
+        tables.append(E.SimpleEmbedding(E.DeviceArray(buf, (DIM, NROWS)), E.Static(DIM)))
+    I_host = make_indices(rng, args.dist, NT, NROWS, BAG, BATCH)
+    distinct = [int(np.unique(I_host[:, :, t]).size) for t in range(NT)]
+    idx_pinned = E.pinned_empty((BAG, BATCH, NT), np.int64)
+    idx_pinned[...] = I_host
+    total_rows = PREPEND + NT * DIM
+    out_pinned = E.pinned_empty((total_rows, BATCH), np.float32)
+    delta_pinned = E.pinned_empty((total_rows, BATCH), np.float32)
+    delta_pinned.reshape(-1, order="F")[:] = rng.standard_normal(total_rows * BATCH, dtype=np.float32)
+
+    I_dev = E.DeviceArray.empty((BAG, BATCH, NT), np.int64).upload(idx_pinned)
+    out_dev = E.DeviceArray.empty((total_rows, BATCH), np.float32)
+    delta_dev = E.DeviceArray.empty((total_rows, BATCH), np.float32).upload(delta_pinned)
+    strategy = E.PreallocationStrategy(PREPEND)
+    indexer = E.Indexer()
+    opt = E.Descent(ETA)
+    S = E.Static(DIM)
+    Is = list(E.colwrap(I_dev))
+    launches = {"fwd": 0, "index": 0, "update": 0}
+
+    def step(events=None):
+        # forward: one fused launch writing straight into the concatenated matrix
+        E.maplookup_(strategy, out_dev, tables, I_dev)
+        launches["fwd"] = lib.etb_last_launch_count()
+        if events: events[1].record()
+        # backward: lazy pullback = row-slice views of the cotangent (no kernel)
+        slicer = E.Slicer(PREPEND + 1, 1, delta_dev)
+        grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is]
+        # update!: index! (batched sort + bucket heads) then fused segment-reduce + SGD
+        E.index_(indexer, tables, grads)
+        launches["index"] = lib.etb_last_launch_count()
+        if events: events[2].record()
+        E.sparseupdate._apply(tables, grads, indexer, opt.eta)
+        launches["update"] = lib.etb_last_launch_count()
+        if events: events[3].record()
+
+    def step_e2e():
+        I_dev.upload(idx_pinned)                          # H2D: this step's indices
+        E.maplookup_(strategy, out_dev, tables, I_dev)
+        out_dev.download(out_pinned)                      # D2H: the step's result (feature matrix)
+        delta_dev.upload(delta_pinned)                    # H2D: the upstream cotangent
+        slicer = E.Slicer(PREPEND + 1, 1, delta_dev)
+        grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is]
+        E.update_(opt, tables, grads, [indexer])
+
+    def sync():
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    end = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        sync()
+        for k in range(K):
+            ev[k][0].record()
+            step(ev[k])
+        end.record()
+        sync()
+    total_ms = ev[0][0].elapsed_time(end)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    index_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    upd_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))
+    ms_per_step = total_ms / K
+    lookups = NT * BATCH * BAG
+
+    # ---- e2e: host buffers in, host result out, every step --------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        step_e2e()
+    e1.record()
+    sync()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / K
+    e2e_ms = max(e0.elapsed_time(e1) / K, e2e_wall_ms)  # host-side work counts too
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    s_, b_ = 4, 8
+    fwd_bytes = NT * BATCH * (BAG * (b_ + DIM * s_) + DIM * s_)                  # pooled fwd
+    u_sum = sum(distinct)
+    upd_kernel_bytes = NT * BATCH * DIM * s_ + 2 * u_sum * DIM * s_ + NT * BATCH * BAG * 4   # delta + row RMW + map
+    upd_total_bytes = NT * BATCH * BAG * b_ + NT * BATCH * DIM * s_ + 2 * u_sum * DIM * s_  # update
+    kernels = {
+        "pooled_kernel": {"ms": fwd_ms, "bytes": fwd_bytes, "gbs": fwd_bytes / fwd_ms / 1e6},
+        "sgd_update_kernel": {"ms": upd_ms, "bytes": upd_kernel_bytes, "gbs": upd_kernel_bytes / upd_ms / 1e6},
+        "index(make_pairs+radix sort+select)": {"ms": index_ms},
+    }
+    dom = "pooled_kernel" if fwd_ms >= upd_ms else "sgd_update_kernel"
+    roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac_of_nominal_8TBs": kernels[dom]["gbs"] / 8000.0}
+
+    cpu = cpu_reference_arm(steps=2, warmup=1, dist=args.dist) if not args.no_cpu_baseline else None
+    gpu_launches = (launches["fwd"] + launches["index"] + launches["update"]) * K
+    line = {
+        "metric": "embedding_lookups_per_sec", "value": lookups / (ms_per_step * 1e-3), "unit": "lookups/s",
+        "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "dist": args.dist, "index_type": "int64", "eta": ETA,
+                   "l2": "inputs larger than L2: 13.3 GB of tables, random rows; no flush needed",
+                   "distinct_rows_per_table_mean": u_sum / NT},
+        "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
+                "d2h_bytes_per_step": int(out_pinned.nbytes)},
+        "gpu_launches": gpu_launches,
+        "launches_per_step": launches,
+        "clocks": clocks.result,
+        "roofline": roof,
+        "kernels": kernels,
+        "fwd_lookups_per_sec": lookups / (fwd_ms * 1e-3),
+        "fwd_bwd_sgd_gbs": (fwd_bytes + upd_total_bytes) / (ms_per_step * 1e6),
+        "fwd_bwd_sgd_frac_of_peak": (fwd_bytes + upd_total_bytes) / (ms_per_step * 1e6) / peak,
+        "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -170,15 +170,23 @@ __device__ __forceinline__ double sgd_epilogue<double>(double row, double acc, d
     return fma ? __fma_rn(-eta, acc, row) : __dsub_rn(row, __dmul_rn(eta, acc));
 }
 
+// One warp owns a TILE of 32 consecutive buckets.  Lane l fetches bucket l's metadata (start,
+// stop, key, first member) with coalesced loads -- one metadata round trip per 32 buckets instead
+// of four dependent loads per bucket.  The warp's 32/G groups then walk the tile's buckets, UB at
+// a time: the old table rows and the first delta row of UB buckets are in flight together; buckets
+// with more than one member (duplicate indices) finish with an ordered loop over the rest.
 template <typename T, int VB, int VPL, typename KeyT>
 __global__ void __launch_bounds__(kUThreads)
 sgd_update_kernel(const __grid_constant__ UpdParams P) {
-    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+    constexpr int UB = (4 / VPL) > 1 ? (4 / VPL) : 1;  // buckets in flight per group
+    constexpr int U = (4 / VPL) > 1 ? (4 / VPL) : 1;   // extra member rows in flight
     using V = Vec<T, VB>;
     const int G = P.G, nvec = P.nvec;
-    const int gl = threadIdx.x & (G - 1);
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const int g = lane / G, ngroups = 32 / G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
     const int64_t nnz = *P.nnz;
-    const int64_t groups_total = (int64_t)gridDim.x * (kUThreads / G);
     const KeyT row_mask = (KeyT)(((KeyT)1 << P.row_bits) - 1);
     const T eta = (T)P.eta;  // convert(eltype(table), opt.eta), reference src/sparseupdate.jl:173
     const bool fma = P.fma != 0;
@@ -189,58 +197,98 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         s_begin = (int64_t)(P.this_split - 1) * split;
         s_end = min((int64_t)P.this_split * split, nnz);
     }
-    for (int64_t s = s_begin + (int64_t)blockIdx.x * (kUThreads / G) + threadIdx.x / G; s < s_end; s += groups_total) {
-        const int64_t start = __ldg(P.offsets + s);
-        const int64_t stop = (s + 1 < nnz) ? __ldg(P.offsets + s + 1) : P.n_total;
-        const KeyT key = __ldg((const KeyT*)P.keys + start);
-        const int slot = (int)(key >> P.row_bits) - P.slot0;
-        if (slot < 0 || slot >= P.nslots) continue;  // bucket of another launch's class
-        const UpdDesc& d = P.item[slot];
-        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(key & row_mask) + 1));
+    const int64_t warps_total = (int64_t)gridDim.x * (kUThreads / 32);
+    const int64_t warp_id = (int64_t)blockIdx.x * (kUThreads / 32) + threadIdx.x / 32;
+
+    for (int64_t t0 = s_begin + warp_id * 32; t0 < s_end; t0 += warps_total * 32) {
+        const int nvalid = (int)min((int64_t)32, s_end - t0);
+        // ---- tile metadata: lane l describes bucket t0 + l (clamped: duplicates are never stored)
+        const int64_t s = t0 + min(lane, nvalid - 1);
+        const int64_t my_start = __ldg(P.offsets + s);
+        const int64_t my_stop = (s + 1 < nnz) ? __ldg(P.offsets + s + 1) : P.n_total;
+        const KeyT my_key = __ldg((const KeyT*)P.keys + my_start);
+        const int my_m0 = __ldg(P.map + my_start);
+        const int my_slot = (int)(my_key >> P.row_bits) - P.slot0;
+        const bool my_mine = my_slot >= 0 && my_slot < P.nslots;  // else: another launch's class
+        const UpdDesc& md = P.item[my_mine ? my_slot : 0];
+        const char* my_row = row_ptr(md.table, (int64_t)(my_key & row_mask) + 1);
+        const char* my_d0 = md.delta + (int64_t)my_m0 * md.ld_delta_bytes;
+        const int my_cnt = (int)min(my_stop - my_start, (int64_t)0x7fffffff);
 
         for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
             int vi[VPL];
 #pragma unroll
             for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
-            // the row's old value is independent of the deltas: fetch it first so its latency
-            // overlaps the accumulation
-            V old[VPL];
+            for (int k0 = 0; k0 < G; k0 += UB) {
+                const char* row[UB];
+                V old[UB][VPL], v0[UB][VPL];
+                int cnt[UB], b[UB], slot[UB];
+                int64_t first[UB];
+                bool mine[UB];
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) ld_plain<VB>(&old[p], row + vi[p]);
-            V acc[VPL];  // accum = zero(Tiled), reference src/sparseupdate.jl:114
+                for (int u = 0; u < UB; ++u) {
+                    b[u] = g + (k0 + u) * ngroups;  // this group's (k0+u)-th bucket of the tile
+                    const int src = min(b[u], nvalid - 1);
+                    row[u] = shfl_ptr(my_row, src, 32);
+                    const char* d0 = shfl_ptr(my_d0, src, 32);
+                    cnt[u] = __shfl_sync(0xffffffffu, my_cnt, src);
+                    first[u] = __shfl_sync(0xffffffffu, my_start, src);
+                    slot[u] = __shfl_sync(0xffffffffu, my_mine ? my_slot : 0, src);
+                    mine[u] = __shfl_sync(0xffffffffu, (int)my_mine, src) != 0;
 #pragma unroll
-            for (int p = 0; p < VPL; ++p)
-#pragma unroll
-                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
-            for (int64_t i0 = start; i0 < stop; i0 += G) {
-                const int m = (int)min((int64_t)G, stop - i0);
-                const char* mine = d.delta + (int64_t)__ldg(P.map + i0 + min(gl, m - 1)) * d.ld_delta_bytes;
-                for (int j0 = 0; j0 < m; j0 += U) {
-                    const char* r[U];
-#pragma unroll
-                    for (int u = 0; u < U; ++u) r[u] = shfl_ptr(mine, min(j0 + u, m - 1), G);
-                    V v[U][VPL];
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-#pragma unroll
-                        for (int p = 0; p < VPL; ++p)
-                            if (u == 0 || j0 + u < m) ld_row<VB>(&v[u][p], r[u] + vi[p]);
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        if (j0 + u < m)
-#pragma unroll
-                            for (int p = 0; p < VPL; ++p)
-#pragma unroll
-                                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[u][p].e[k];
+                    for (int p = 0; p < VPL; ++p) {
+                        ld_plain<VB>(&old[u][p], row[u] + vi[p]);
+                        ld_row<VB>(&v0[u][p], d0 + vi[p]);
+                    }
                 }
-            }
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) {
-                if (pass0 + gl + p * G < nvec) {
-                    V out;
+                for (int u = 0; u < UB; ++u) {
+                    V acc[VPL];  // accum = zero(Tiled) then += members in order (src/sparseupdate.jl:114-120)
 #pragma unroll
-                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, fma);
-                    *(V*)(row + vi[p]) = out;
+                    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                        for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0) + v0[u][p].e[k];
+                    if (cnt[u] > 1) {  // duplicates: the rest of the bucket, strictly in order
+                        // (groups of one warp diverge here when G < 32: shuffles use the group mask)
+                        const UpdDesc& d = P.item[slot[u]];
+                        const int64_t stop = first[u] + cnt[u];
+                        for (int64_t i0 = first[u] + 1; i0 < stop; i0 += G) {
+                            const int m = (int)min((int64_t)G, stop - i0);
+                            const char* mine_d = d.delta + (int64_t)__ldg(P.map + i0 + min(gl, m - 1)) * d.ld_delta_bytes;
+                            for (int j0 = 0; j0 < m; j0 += U) {
+                                V v[U][VPL];
+#pragma unroll
+                                for (int w = 0; w < U; ++w) {
+                                    const unsigned long long pv = (unsigned long long)mine_d;
+                                    const int sl = (lane & ~(G - 1)) + min(j0 + w, m - 1);
+                                    const unsigned lo = __shfl_sync(gmask, (unsigned)pv, sl);
+                                    const unsigned hi = __shfl_sync(gmask, (unsigned)(pv >> 32), sl);
+                                    const char* r = (const char*)(((unsigned long long)hi << 32) | lo);
+#pragma unroll
+                                    for (int p = 0; p < VPL; ++p) ld_row<VB>(&v[w][p], r + vi[p]);
+                                }
+#pragma unroll
+                                for (int w = 0; w < U; ++w)
+                                    if (j0 + w < m)
+#pragma unroll
+                                        for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                                            for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
+                            }
+                        }
+                    }
+                    if (b[u] < nvalid && mine[u]) {
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) {
+                            if (pass0 + gl + p * G < nvec) {
+                                V out;
+#pragma unroll
+                                for (int k = 0; k < V::NE; ++k)
+                                    out.e[k] = sgd_epilogue<T>(old[u][p].e[k], acc[p].e[k], eta, fma);
+                                *(V*)(const_cast<char*>(row[u]) + vi[p]) = out;
+                            }
+                        }
+                    }
                 }
             }
         }
@@ -435,9 +483,9 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         P.nslots = n;
         P.G = c.G;
         P.nvec = c.nvec;
-        const int64_t groups_per_block = kUThreads / c.G;
-        const int64_t want = (view->n_total + groups_per_block - 1) / groups_per_block;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 8);  // persistent, grid-stride over buckets
+        const int64_t buckets_per_block = (kUThreads / 32) * 32;  // one 32-bucket tile per warp
+        const int64_t want = (view->n_total + buckets_per_block - 1) / buckets_per_block;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 16);  // grid-stride over bucket tiles
         if (view->key_bytes == 4) {
             if (c.elt == ETB_F32) launch_update_vb<float, uint32_t>(c, grid, stream, P);
             else launch_update_vb<double, uint32_t>(c, grid, stream, P);

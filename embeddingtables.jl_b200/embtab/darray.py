@@ -138,6 +138,20 @@ class DeviceArray:
             torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))))
         return self
 
+    def upload(self, host: np.ndarray) -> "DeviceArray":
+        """Asynchronous host->device copy on the current stream.  `host` holds this array's
+        elements in column-major memory order (e.g. a pinned buffer from `pinned_empty`); the
+        copy is truly asynchronous only from pinned memory."""
+        assert self.is_dense and host.dtype == self.dtype and host.size == int(np.prod(self.shape))
+        _lib.check(_lib.lib().etb_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, current_stream_ptr()))
+        return self
+
+    def download(self, host: np.ndarray) -> np.ndarray:
+        """Asynchronous device->host copy on the current stream (synchronise before reading)."""
+        assert self.is_dense and host.dtype == self.dtype and host.size == int(np.prod(self.shape))
+        _lib.check(_lib.lib().etb_memcpy_d2h(host.ctypes.data, self.ptr, host.nbytes, current_stream_ptr()))
+        return host
+
     def fill(self, v):
         if self.is_dense:
             n = int(np.prod(self.shape)) if self.shape else 1
@@ -161,6 +175,18 @@ class DeviceArray:
 
     def __repr__(self):
         return f"DeviceArray{self.shape}<{self.dtype}, ld={self.ld}>"
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A page-locked host array (Fortran order, Julia shape) for asynchronous upload/download."""
+    shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+    t = torch.empty(int(np.prod(shape)), dtype=_NP2T[np.dtype(dtype)], pin_memory=True)
+    a = t.numpy().reshape(shape, order="F")
+    _PINNED_KEEPALIVE[a.ctypes.data] = t
+    return a
+
+
+_PINNED_KEEPALIVE = {}
 
 
 def as_device(a, dtype=None) -> DeviceArray:

@@ -88,7 +88,7 @@ def _ld(a):
     """leading dimension (elements) of a Fortran-ordered 2-D array or view."""
     if a.ndim == 1:
         return a.shape[0]
-    assert a.strides[0] == a.itemsize, "feature vectors must be contiguous"
+    assert a.shape[0] == 1 or a.strides[0] == a.itemsize, "feature vectors must be contiguous"
     return max(a.strides[1] // a.itemsize, a.shape[0]) if a.shape[1] > 1 else a.shape[0]
 
 
