@@ -101,13 +101,16 @@ struct alignas(VB) Vec {
     T e[NE];
 };
 
-// read-only, table rows: keep in L2 (Zipf reuse), do not pollute L1
+// Read-only row loads through the non-coherent path with the DEFAULT L2 policy.  Measured on
+// B200 (profiles/r1a): adding `.L1::no_allocate` makes the sectors evict_first in L2, and rows
+// that are re-read (the cotangent slice in update!, hot Zipf rows in lookups) then miss L2 --
+// +5.6 GB of DRAM reads on C2's update.
 template <int VB>
 __device__ __forceinline__ void ld_row(void* out, const char* p);
 template <>
 __device__ __forceinline__ void ld_row<16>(void* out, const char* p) {
     uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p));
     *(uint4*)out = v;
@@ -115,13 +118,13 @@ __device__ __forceinline__ void ld_row<16>(void* out, const char* p) {
 template <>
 __device__ __forceinline__ void ld_row<8>(void* out, const char* p) {
     uint2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     *(uint2*)out = v;
 }
 template <>
 __device__ __forceinline__ void ld_row<4>(void* out, const char* p) {
     uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
     *(uint32_t*)out = v;
 }
 

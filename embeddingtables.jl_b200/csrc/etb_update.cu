@@ -264,8 +264,9 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                                     const unsigned lo = __shfl_sync(gmask, (unsigned)pv, sl);
                                     const unsigned hi = __shfl_sync(gmask, (unsigned)(pv >> 32), sl);
                                     const char* r = (const char*)(((unsigned long long)hi << 32) | lo);
+                                    if (w == 0 || j0 + w < m)  // no duplicate traffic for the clamped tail
 #pragma unroll
-                                    for (int p = 0; p < VPL; ++p) ld_row<VB>(&v[w][p], r + vi[p]);
+                                        for (int p = 0; p < VPL; ++p) ld_row<VB>(&v[w][p], r + vi[p]);
                                 }
 #pragma unroll
                                 for (int w = 0; w < U; ++w)
