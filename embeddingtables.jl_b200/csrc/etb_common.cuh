@@ -148,12 +148,36 @@ __device__ __forceinline__ void st_stream<4>(char* p, const void* in) {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// plain (cacheable) vector load/store used for read-modify-write of table rows
+// coherent global vector load/store for the read-modify-write of table rows (explicit
+// ld.global/st.global: a pointer fetched from a descriptor would otherwise compile to a generic LD/ST)
 template <int VB>
 __device__ __forceinline__ void ld_plain(void* out, const char* p) {
-    if constexpr (VB == 16) *(uint4*)out = *(const uint4*)p;
-    else if constexpr (VB == 8) *(uint2*)out = *(const uint2*)p;
-    else *(uint32_t*)out = *(const uint32_t*)p;
+    if constexpr (VB == 16) {
+        uint4 v;
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+        *(uint4*)out = v;
+    } else if constexpr (VB == 8) {
+        uint2 v;
+        asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+        *(uint2*)out = v;
+    } else {
+        uint32_t v;
+        asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+        *(uint32_t*)out = v;
+    }
+}
+template <int VB>
+__device__ __forceinline__ void st_plain(char* p, const void* in) {
+    if constexpr (VB == 16) {
+        const uint4 v = *(const uint4*)in;
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    } else if constexpr (VB == 8) {
+        const uint2 v = *(const uint2*)in;
+        asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+    } else {
+        const uint32_t v = *(const uint32_t*)in;
+        asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    }
 }
 
 template <typename IdxT>

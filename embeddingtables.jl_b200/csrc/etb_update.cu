@@ -23,6 +23,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 #include <vector>
 
 #include "etb_common.cuh"
@@ -30,13 +31,39 @@
 namespace etb {
 
 constexpr int kUThreads = 256;
+#ifndef ETB_UPDATE_UB
+#define ETB_UPDATE_UB 8
+#endif
+#ifndef ETB_UPDATE_U
+#define ETB_UPDATE_U 1
+#endif
+#ifndef ETB_UPDATE_MIN_BLOCKS
+#define ETB_UPDATE_MIN_BLOCKS 2
+#endif
 constexpr int kUMaxItems = 96;
 
 // ------------------------------------------------------------------------------------ layout
+// One record per bucket, written by K4 and read by K5 with ONE coalesced load per 32 buckets
+// (the reference's `cumulative` entry (col, offset), src/utils.jl:340-345, plus the first member).
+struct alignas(16) BucketRec {
+    uint32_t start;  // first sorted position of the bucket
+    int32_t m0;      // delta column of its first member
+    uint64_t key;    // slot << row_bits | (row - 1)
+};
+
+// long-bucket bookkeeping of ETB_UPDATE_SPLIT_LONG
+constexpr int kLongThreshold = 128;  // buckets with more members than this are "long"
+constexpr int kLongChunk = 128;      // members per partial sum
+struct LongCounters { uint32_t n_long, n_chunks; };
+struct LongRec { uint32_t bucket, chunk_base, nchunks, pad; };
+struct ChunkRec { uint32_t long_id, chunk; };
+
 struct IndexLayout {
     int64_t n_total;
     int32_t row_bits, slot_bits, key_bytes;
-    size_t off_keys[2], off_vals[2], off_offsets, off_nnz, off_temp, temp_bytes, total;
+    size_t max_long, max_chunks, partial_pitch;
+    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_counters, off_long, off_chunks, off_partials, off_temp,
+        temp_bytes, total;
 };
 
 static int bits_for(uint64_t count) {  // bits needed to represent 0 .. count-1
@@ -47,19 +74,38 @@ static int bits_for(uint64_t count) {  // bits needed to represent 0 .. count-1
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-struct HeadPred32 {
-    const uint32_t* keys;
-    __device__ __forceinline__ bool operator()(int64_t p) const { return p == 0 || keys[p] != keys[p - 1]; }
+template <typename KeyT>
+struct MakeRec {
+    const KeyT* keys;
+    const int32_t* map;
+    __device__ __forceinline__ BucketRec operator()(int32_t p) const {
+        BucketRec r;
+        r.start = (uint32_t)p;
+        r.m0 = map[p];
+        r.key = (uint64_t)keys[p];
+        return r;
+    }
 };
-struct HeadPred64 {
-    const uint64_t* keys;
-    __device__ __forceinline__ bool operator()(int64_t p) const { return p == 0 || keys[p] != keys[p - 1]; }
+template <typename KeyT>
+struct IsHead {
+    const KeyT* keys;
+    __device__ __forceinline__ bool operator()(const BucketRec& r) const {
+        return r.start == 0 || (uint64_t)keys[r.start - 1] != r.key;
+    }
 };
+
+template <typename KeyT>
+static cudaError_t select_heads(void* temp, size_t& temp_bytes, const KeyT* keys, const int32_t* map, BucketRec* recs,
+                                int64_t* nnz, int64_t n, cudaStream_t stream) {
+    auto in = thrust::make_transform_iterator(thrust::counting_iterator<int32_t>(0), MakeRec<KeyT>{keys, map});
+    return cub::DeviceSelect::If(temp, temp_bytes, in, recs, nnz, (int32_t)n, IsHead<KeyT>{keys}, stream);
+}
 
 static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexLayout& L) {
     ETB_REQUIRE(n_items >= 0, "etb_index: negative item count");
     ETB_REQUIRE(n_items == 0 || items, "etb_index: null items");
     int64_t n_total = 0, max_rows = 1;
+    size_t max_row_bytes = 16;
     for (int i = 0; i < n_items; ++i) {
         const etb_update_item& it = items[i];
         if (int32_t st = validate_table(it.table, "etb_index")) return st;
@@ -69,6 +115,7 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
         ETB_REQUIRE(it.bag == 0 || it.ld_idx >= it.bag, "etb_index: item %d: ld_idx < bag", i);
         n_total += it.batch * (it.bag ? it.bag : 1);
         max_rows = std::max(max_rows, it.table.nrows);
+        max_row_bytes = std::max(max_row_bytes, (size_t)it.table.dim * elt_bytes(it.table.elt));
     }
     ETB_REQUIRE(n_total < 0x7fffffffll, "etb_index: %lld occurrences exceed the 2^31 limit of one call", (long long)n_total);
     L.n_total = n_total;
@@ -77,11 +124,18 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     ETB_REQUIRE(L.row_bits + L.slot_bits <= 64, "etb_index: key does not fit 64 bits");
     L.key_bytes = (L.row_bits + L.slot_bits <= 32) ? 4 : 8;
     const size_t n = (size_t)std::max<int64_t>(n_total, 1);
+    L.max_long = n / kLongThreshold + 1;
+    L.max_chunks = n / kLongChunk + L.max_long;
+    L.partial_pitch = align_up(max_row_bytes, 16);
     size_t off = 0;
     for (int b = 0; b < 2; ++b) { L.off_keys[b] = off; off = align_up(off + n * L.key_bytes); }
     for (int b = 0; b < 2; ++b) { L.off_vals[b] = off; off = align_up(off + n * sizeof(int32_t)); }
-    L.off_offsets = off; off = align_up(off + (n + 1) * sizeof(int64_t));
+    L.off_recs = off; off = align_up(off + (n + 1) * sizeof(BucketRec));
     L.off_nnz = off; off = align_up(off + sizeof(int64_t));
+    L.off_counters = off; off = align_up(off + sizeof(LongCounters));
+    L.off_long = off; off = align_up(off + L.max_long * sizeof(LongRec));
+    L.off_chunks = off; off = align_up(off + L.max_chunks * sizeof(ChunkRec));
+    L.off_partials = off; off = align_up(off + L.max_chunks * L.partial_pitch);
     // CUB temp storage: max over the sort and the select
     size_t t_sort = 0, t_sel = 0;
     const int end_bit = L.row_bits + L.slot_bits;
@@ -89,14 +143,12 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
         cub::DoubleBuffer<uint32_t> k(nullptr, nullptr);
         cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
         ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
-        ETB_CUDA(cub::DeviceSelect::If(nullptr, t_sel, thrust::counting_iterator<int64_t>(0), (int64_t*)nullptr,
-                                       (int64_t*)nullptr, (int64_t)n, HeadPred32{nullptr}));
+        ETB_CUDA(select_heads<uint32_t>(nullptr, t_sel, nullptr, nullptr, nullptr, nullptr, (int64_t)n, 0));
     } else {
         cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
         cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
         ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
-        ETB_CUDA(cub::DeviceSelect::If(nullptr, t_sel, thrust::counting_iterator<int64_t>(0), (int64_t*)nullptr,
-                                       (int64_t*)nullptr, (int64_t)n, HeadPred64{nullptr}));
+        ETB_CUDA(select_heads<uint64_t>(nullptr, t_sel, nullptr, nullptr, nullptr, nullptr, (int64_t)n, 0));
     }
     L.off_temp = off;
     L.temp_bytes = std::max(t_sort, t_sel);
@@ -144,16 +196,20 @@ struct UpdDesc {  // 48 bytes
 };
 struct UpdParams {
     UpdDesc item[kUMaxItems];
-    const void* keys;
+    const BucketRec* recs;
     const int32_t* map;
-    const int64_t* offsets;
     const int64_t* nnz;
+    LongCounters* counters;
+    LongRec* longs;
+    ChunkRec* chunks;
+    char* partials;
+    int64_t partial_pitch;
     int64_t n_total;
     double eta;
     int32_t row_bits;
     int32_t slot0, nslots;  // this launch handles slots [slot0, slot0 + nslots)
     int32_t G, nvec;
-    int32_t fma;
+    int32_t fma, split_long;
     int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:564-572
 };
 
@@ -170,24 +226,95 @@ __device__ __forceinline__ double sgd_epilogue<double>(double row, double acc, d
     return fma ? __fma_rn(-eta, acc, row) : __dsub_rn(row, __dmul_rn(eta, acc));
 }
 
-// One warp owns a TILE of 32 consecutive buckets.  Lane l fetches bucket l's metadata (start,
-// stop, key, first member) with coalesced loads -- one metadata round trip per 32 buckets instead
-// of four dependent loads per bucket.  The warp's 32/G groups then walk the tile's buckets, UB at
-// a time: the old table rows and the first delta row of UB buckets are in flight together; buckets
-// with more than one member (duplicate indices) finish with an ordered loop over the rest.
-template <typename T, int VB, int VPL, typename KeyT>
-__global__ void __launch_bounds__(kUThreads)
-sgd_update_kernel(const __grid_constant__ UpdParams P) {
-    constexpr int UB = (4 / VPL) > 1 ? (4 / VPL) : 1;  // buckets in flight per group
-    constexpr int U = (4 / VPL) > 1 ? (4 / VPL) : 1;   // extra member rows in flight
+__device__ __forceinline__ unsigned group_mask(int G, int lane) {
+    return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+}
+
+__device__ __forceinline__ const char* shfl_ptr_mask(unsigned mask, const char* p, int src_lane) {
+    unsigned long long v = (unsigned long long)p;
+    unsigned lo = __shfl_sync(mask, (unsigned)v, src_lane);
+    unsigned hi = __shfl_sync(mask, (unsigned)(v >> 32), src_lane);
+    return (const char*)(((unsigned long long)hi << 32) | lo);
+}
+
+// acc += delta[:, map[i]] for i in [i0, stop), strictly in order, U rows in flight.
+// All lanes of the calling group are converged; shuffles stay inside the group.
+template <typename T, int VB, int VPL, int U>
+__device__ __forceinline__ void accumulate_members(Vec<T, VB> (&acc)[VPL], const UpdDesc& d, const int32_t* map,
+                                                   int64_t i0, int64_t stop, const int (&vi)[VPL], int G, int gl,
+                                                   int lane, unsigned gmask) {
     using V = Vec<T, VB>;
+    for (; i0 < stop; i0 += G) {
+        const int m = (int)min((int64_t)G, stop - i0);
+        const char* mine_d = d.delta + (int64_t)__ldg(map + i0 + min(gl, m - 1)) * d.ld_delta_bytes;
+        for (int j0 = 0; j0 < m; j0 += U) {
+            V v[U][VPL];
+#pragma unroll
+            for (int w = 0; w < U; ++w) {
+                const char* r = shfl_ptr_mask(gmask, mine_d, (lane & ~(G - 1)) + min(j0 + w, m - 1));
+                if (w == 0 || j0 + w < m)  // no duplicate traffic for the clamped tail
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p) ld_row<VB>(&v[w][p], r + vi[p]);
+            }
+#pragma unroll
+            for (int w = 0; w < U; ++w)
+                if (j0 + w < m)
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                        for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
+        }
+    }
+}
+
+// One warp owns a TILE of 32 consecutive buckets.  Lane l fetches bucket l's record with one
+// coalesced load (start, key, first member), resolves the row and first-delta addresses and parks
+// them in shared memory -- one metadata round trip per 32 buckets, one LDS.128 per bucket later.
+// Each group of G lanes then walks the G buckets of its own lanes:
+// UB buckets at a time, old table row + first delta row of all UB in flight together; buckets with
+// duplicates then add their remaining members strictly in order (those rows come from L2).
+// Tiles are taken in bucket order = (table, row) order, one tile per warp (no grid-stride loop):
+// the warps resident at any moment then work inside ONE table, so the delta rows they re-read
+// (that table's slice of the cotangent) stay L2-resident.  nnz lives on the device: the grid is
+// sized for the upper bound n_total and surplus warps exit.
+// hand a bucket to the long path: fixed-size chunks, combined in chunk order (cold; kept out of line
+// so that it costs the hot loop no registers)
+__device__ __noinline__ void register_long_bucket(LongCounters* counters, LongRec* longs, ChunkRec* chunks,
+                                                  uint32_t bucket, int cnt) {
+    const uint32_t nch = (uint32_t)((cnt + kLongChunk - 1) / kLongChunk);
+    const uint32_t j = atomicAdd(&counters->n_long, 1u);
+    const uint32_t cb = atomicAdd(&counters->n_chunks, nch);
+    longs[j] = LongRec{bucket, cb, nch, 0u};
+    for (uint32_t c = 0; c < nch; ++c) chunks[cb + c] = ChunkRec{j, c};
+}
+
+struct alignas(16) TileMeta {
+    const char* row;  // table row of the bucket
+    const char* d0;   // delta row of its first member
+};
+struct alignas(16) TileMeta2 {
+    uint32_t start;
+    int32_t cnt;   // members; 0 = nothing to do for this launch (invalid / other class / long)
+    int32_t slot;
+    int32_t pad;
+};
+
+template <typename T, int VB, int VPL>
+__global__ void __launch_bounds__(kUThreads, ETB_UPDATE_MIN_BLOCKS)
+sgd_update_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int UB = (ETB_UPDATE_UB / VPL) > 1 ? (ETB_UPDATE_UB / VPL) : 1;  // buckets in flight per group
+    constexpr int U = (ETB_UPDATE_U / VPL) > 1 ? (ETB_UPDATE_U / VPL) : 1;  // extra member rows in flight
+    using V = Vec<T, VB>;
+    __shared__ TileMeta s_meta[kUThreads];
+    __shared__ TileMeta2 s_meta2[kUThreads];
     const int G = P.G, nvec = P.nvec;
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
-    const int g = lane / G, ngroups = 32 / G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
+    const int wbase = threadIdx.x & ~31;            // this warp's slice of the shared arrays
+    const int gbase = wbase + (lane & ~(G - 1));    // this group's slice
+    const unsigned gmask = group_mask(G, lane);
     const int64_t nnz = *P.nnz;
-    const KeyT row_mask = (KeyT)(((KeyT)1 << P.row_bits) - 1);
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
     const T eta = (T)P.eta;  // convert(eltype(table), opt.eta), reference src/sparseupdate.jl:173
     const bool fma = P.fma != 0;
 
@@ -197,99 +324,175 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         s_begin = (int64_t)(P.this_split - 1) * split;
         s_end = min((int64_t)P.this_split * split, nnz);
     }
-    const int64_t warps_total = (int64_t)gridDim.x * (kUThreads / 32);
     const int64_t warp_id = (int64_t)blockIdx.x * (kUThreads / 32) + threadIdx.x / 32;
+    const int64_t t0 = s_begin + warp_id * 32;
+    if (t0 >= s_end) return;
 
-    for (int64_t t0 = s_begin + warp_id * 32; t0 < s_end; t0 += warps_total * 32) {
-        const int nvalid = (int)min((int64_t)32, s_end - t0);
-        // ---- tile metadata: lane l describes bucket t0 + l (clamped: duplicates are never stored)
-        const int64_t s = t0 + min(lane, nvalid - 1);
-        const int64_t my_start = __ldg(P.offsets + s);
-        const int64_t my_stop = (s + 1 < nnz) ? __ldg(P.offsets + s + 1) : P.n_total;
-        const KeyT my_key = __ldg((const KeyT*)P.keys + my_start);
-        const int my_m0 = __ldg(P.map + my_start);
-        const int my_slot = (int)(my_key >> P.row_bits) - P.slot0;
-        const bool my_mine = my_slot >= 0 && my_slot < P.nslots;  // else: another launch's class
-        const UpdDesc& md = P.item[my_mine ? my_slot : 0];
-        const char* my_row = row_ptr(md.table, (int64_t)(my_key & row_mask) + 1);
-        const char* my_d0 = md.delta + (int64_t)my_m0 * md.ld_delta_bytes;
-        const int my_cnt = (int)min(my_stop - my_start, (int64_t)0x7fffffff);
+    {   // ---- tile metadata: lane l describes bucket t0 + l
+        const bool valid = t0 + lane < s_end;
+        const int64_t s = valid ? t0 + lane : s_end - 1;
+        const uint4 raw = __ldg((const uint4*)(P.recs + s));
+        const int64_t start = raw.x;
+        const int64_t stop = (s + 1 < nnz) ? (int64_t)__ldg(&P.recs[s + 1].start) : P.n_total;
+        const uint64_t key = ((uint64_t)raw.w << 32) | raw.z;
+        const int slot = (int)(key >> P.row_bits) - P.slot0;
+        const bool mine = valid && slot >= 0 && slot < P.nslots;  // else another launch's class
+        const UpdDesc& md = P.item[mine ? slot : 0];
+        int cnt = mine ? (int)(stop - start) : 0;
+        if (P.split_long && cnt > kLongThreshold) {
+            register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            cnt = 0;
+        }
+        TileMeta m;
+        m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
+        m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
+        s_meta[threadIdx.x] = m;
+        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, 0};
+    }
+    __syncwarp();
 
-        for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
-            int vi[VPL];
+    for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
+        int vi[VPL];
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
-            for (int k0 = 0; k0 < G; k0 += UB) {
-                const char* row[UB];
-                V old[UB][VPL], v0[UB][VPL];
-                int cnt[UB], b[UB], slot[UB];
-                int64_t first[UB];
-                bool mine[UB];
+        for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
+
+        for (int k0 = 0; k0 < G; k0 += UB) {
+            // the old table row and the first delta row of UB buckets, all in flight together
+            V old[UB][VPL], v0[UB][VPL];
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    b[u] = g + (k0 + u) * ngroups;  // this group's (k0+u)-th bucket of the tile
-                    const int src = min(b[u], nvalid - 1);
-                    row[u] = shfl_ptr(my_row, src, 32);
-                    const char* d0 = shfl_ptr(my_d0, src, 32);
-                    cnt[u] = __shfl_sync(0xffffffffu, my_cnt, src);
-                    first[u] = __shfl_sync(0xffffffffu, my_start, src);
-                    slot[u] = __shfl_sync(0xffffffffu, my_mine ? my_slot : 0, src);
-                    mine[u] = __shfl_sync(0xffffffffu, (int)my_mine, src) != 0;
+            for (int u = 0; u < UB; ++u) {
+                if (k0 + u < G && s_meta2[gbase + k0 + u].cnt > 0) {
+                    const TileMeta m = s_meta[gbase + k0 + u];
 #pragma unroll
                     for (int p = 0; p < VPL; ++p) {
-                        ld_plain<VB>(&old[u][p], row[u] + vi[p]);
-                        ld_row<VB>(&v0[u][p], d0 + vi[p]);
+                        ld_plain<VB>(&old[u][p], m.row + vi[p]);
+                        ld_row<VB>(&v0[u][p], m.d0 + vi[p]);
                     }
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < UB; ++u) {
-                    V acc[VPL];  // accum = zero(Tiled) then += members in order (src/sparseupdate.jl:114-120)
+            for (int u = 0; u < UB; ++u) {
+                if (k0 + u < G) {
+                    const TileMeta2 m2 = s_meta2[gbase + k0 + u];
+                    if (m2.cnt > 0) {
+                        V acc[VPL];  // accum = zero(Tiled), then += members in order (src/sparseupdate.jl:114-120)
 #pragma unroll
-                    for (int p = 0; p < VPL; ++p)
+                        for (int p = 0; p < VPL; ++p)
 #pragma unroll
-                        for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0) + v0[u][p].e[k];
-                    if (cnt[u] > 1) {  // duplicates: the rest of the bucket, strictly in order
-                        // (groups of one warp diverge here when G < 32: shuffles use the group mask)
-                        const UpdDesc& d = P.item[slot[u]];
-                        const int64_t stop = first[u] + cnt[u];
-                        for (int64_t i0 = first[u] + 1; i0 < stop; i0 += G) {
-                            const int m = (int)min((int64_t)G, stop - i0);
-                            const char* mine_d = d.delta + (int64_t)__ldg(P.map + i0 + min(gl, m - 1)) * d.ld_delta_bytes;
-                            for (int j0 = 0; j0 < m; j0 += U) {
-                                V v[U][VPL];
-#pragma unroll
-                                for (int w = 0; w < U; ++w) {
-                                    const unsigned long long pv = (unsigned long long)mine_d;
-                                    const int sl = (lane & ~(G - 1)) + min(j0 + w, m - 1);
-                                    const unsigned lo = __shfl_sync(gmask, (unsigned)pv, sl);
-                                    const unsigned hi = __shfl_sync(gmask, (unsigned)(pv >> 32), sl);
-                                    const char* r = (const char*)(((unsigned long long)hi << 32) | lo);
-                                    if (w == 0 || j0 + w < m)  // no duplicate traffic for the clamped tail
-#pragma unroll
-                                        for (int p = 0; p < VPL; ++p) ld_row<VB>(&v[w][p], r + vi[p]);
-                                }
-#pragma unroll
-                                for (int w = 0; w < U; ++w)
-                                    if (j0 + w < m)
-#pragma unroll
-                                        for (int p = 0; p < VPL; ++p)
-#pragma unroll
-                                            for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
-                            }
-                        }
-                    }
-                    if (b[u] < nvalid && mine[u]) {
+                            for (int e = 0; e < V::NE; ++e) acc[p].e[e] = T(0) + v0[u][p].e[e];
+                        if (m2.cnt > 1)  // duplicates: the rest of the bucket, strictly in order
+                            accumulate_members<T, VB, VPL, U>(acc, P.item[m2.slot], P.map, (int64_t)m2.start + 1,
+                                                              (int64_t)m2.start + m2.cnt, vi, G, gl, lane, gmask);
+                        char* row = const_cast<char*>(s_meta[gbase + k0 + u].row);
 #pragma unroll
                         for (int p = 0; p < VPL; ++p) {
                             if (pass0 + gl + p * G < nvec) {
                                 V out;
 #pragma unroll
-                                for (int k = 0; k < V::NE; ++k)
-                                    out.e[k] = sgd_epilogue<T>(old[u][p].e[k], acc[p].e[k], eta, fma);
-                                *(V*)(const_cast<char*>(row[u]) + vi[p]) = out;
+                                for (int e = 0; e < V::NE; ++e)
+                                    out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[p].e[e], eta, fma);
+                                st_plain<VB>(row + vi[p], &out);
                             }
                         }
                     }
+                }
+            }
+        }
+    }
+}
+
+// ETB_UPDATE_SPLIT_LONG, phase A: one group per (long bucket, chunk): the chunk's members summed
+// strictly in order from zero into a partial row.
+template <typename T, int VB, int VPL>
+__global__ void __launch_bounds__(kUThreads)
+long_partials_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+    using V = Vec<T, VB>;
+    const int G = P.G, nvec = P.nvec;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask(G, lane);
+    const uint32_t n_chunks = P.counters->n_chunks;
+    const int64_t nnz = *P.nnz;
+    const uint32_t groups_total = gridDim.x * (kUThreads / G);
+    for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_chunks; i += groups_total) {
+        const ChunkRec cr = P.chunks[i];
+        const LongRec lr = P.longs[cr.long_id];
+        const BucketRec rec = P.recs[lr.bucket];
+        const int64_t stop_all = ((int64_t)lr.bucket + 1 < nnz) ? (int64_t)P.recs[lr.bucket + 1].start : P.n_total;
+        const int64_t a = (int64_t)rec.start + (int64_t)cr.chunk * kLongChunk;
+        const int64_t b = min(a + kLongChunk, stop_all);
+        const UpdDesc& d = P.item[(int)(rec.key >> P.row_bits) - P.slot0];
+        char* out = P.partials + (int64_t)(lr.chunk_base + cr.chunk) * P.partial_pitch;
+        for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
+            int vi[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
+            V acc[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
+            accumulate_members<T, VB, VPL, U>(acc, d, P.map, a, b, vi, G, gl, lane, gmask);
+#pragma unroll
+            for (int p = 0; p < VPL; ++p)
+                if (pass0 + gl + p * G < nvec) st_plain<VB>(out + vi[p], &acc[p]);
+        }
+    }
+}
+
+// phase B: one group per long bucket: partials added in chunk order from zero, then the epilogue.
+template <typename T, int VB, int VPL>
+__global__ void __launch_bounds__(kUThreads)
+long_combine_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+    using V = Vec<T, VB>;
+    const int G = P.G, nvec = P.nvec;
+    const int gl = threadIdx.x & (G - 1);
+    const uint32_t n_long = P.counters->n_long;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    const T eta = (T)P.eta;
+    const bool fma = P.fma != 0;
+    const uint32_t groups_total = gridDim.x * (kUThreads / G);
+    for (uint32_t j = blockIdx.x * (kUThreads / G) + threadIdx.x / G; j < n_long; j += groups_total) {
+        const LongRec lr = P.longs[j];
+        const BucketRec rec = P.recs[lr.bucket];
+        const UpdDesc& d = P.item[(int)(rec.key >> P.row_bits) - P.slot0];
+        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
+        const char* part = P.partials + (int64_t)lr.chunk_base * P.partial_pitch;
+        for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
+            int vi[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
+            V old[VPL], acc[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) {
+                ld_plain<VB>(&old[p], row + vi[p]);
+#pragma unroll
+                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
+            }
+            for (uint32_t c0 = 0; c0 < lr.nchunks; c0 += U) {
+                V v[U][VPL];
+#pragma unroll
+                for (int w = 0; w < U; ++w)
+                    if (c0 + w < lr.nchunks)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) ld_plain<VB>(&v[w][p], part + (int64_t)(c0 + w) * P.partial_pitch + vi[p]);
+#pragma unroll
+                for (int w = 0; w < U; ++w)
+                    if (c0 + w < lr.nchunks)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                            for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
+            }
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) {
+                if (pass0 + gl + p * G < nvec) {
+                    V out;
+#pragma unroll
+                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, fma);
+                    st_plain<VB>(row + vi[p], &out);
                 }
             }
         }
@@ -329,22 +532,36 @@ static UpdClass classify_update(const etb_update_item& it) {
     return c;
 }
 
-template <typename T, int VB, typename KeyT>
-static void launch_update_vpl(int vpl, int grid, cudaStream_t s, const UpdParams& P) {
+enum { kKernelMain = 0, kKernelPartials = 1, kKernelCombine = 2 };
+
+template <typename T, int VB, int VPL>
+static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
+    if (which == kKernelMain) sgd_update_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
+    else if (which == kKernelPartials) long_partials_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
+    else long_combine_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
+}
+
+template <typename T, int VB>
+static void launch_update_vpl(int which, int vpl, int grid, cudaStream_t s, const UpdParams& P) {
     switch (vpl) {
-        case 1: sgd_update_kernel<T, VB, 1, KeyT><<<grid, kUThreads, 0, s>>>(P); break;
-        case 2: sgd_update_kernel<T, VB, 2, KeyT><<<grid, kUThreads, 0, s>>>(P); break;
-        default: sgd_update_kernel<T, VB, 4, KeyT><<<grid, kUThreads, 0, s>>>(P); break;
+        case 1: launch_update_one<T, VB, 1>(which, grid, s, P); break;
+        case 2: launch_update_one<T, VB, 2>(which, grid, s, P); break;
+        default: launch_update_one<T, VB, 4>(which, grid, s, P); break;
     }
 }
 
-template <typename T, typename KeyT>
-static void launch_update_vb(const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+template <typename T>
+static void launch_update_vb(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     if constexpr (sizeof(T) == 4) {
-        if (c.vb == 4) return launch_update_vpl<T, 4, KeyT>(c.vpl, grid, s, P);
+        if (c.vb == 4) return launch_update_vpl<T, 4>(which, c.vpl, grid, s, P);
     }
-    if (c.vb == 8) return launch_update_vpl<T, 8, KeyT>(c.vpl, grid, s, P);
-    return launch_update_vpl<T, 16, KeyT>(c.vpl, grid, s, P);
+    if (c.vb == 8) return launch_update_vpl<T, 8>(which, c.vpl, grid, s, P);
+    return launch_update_vpl<T, 16>(which, c.vpl, grid, s, P);
+}
+
+static void launch_update(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+    if (c.elt == ETB_F32) launch_update_vb<float>(which, c, grid, s, P);
+    else launch_update_vb<double>(which, c, grid, s, P);
 }
 
 static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int32_t n_items,
@@ -352,10 +569,11 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
     IndexLayout L;
     if (int32_t st = make_layout(items, n_items, L)) return st;
     ETB_REQUIRE(ws != nullptr, "etb_index: null workspace");
+    ETB_REQUIRE(((uintptr_t)ws % 256) == 0, "etb_index: workspace must be 256-byte aligned");
     if (ws_bytes < L.total)
         return fail(ETB_ERR_WORKSPACE, "etb_index: workspace has %zu bytes, needs %zu", ws_bytes, L.total);
     char* base = (char*)ws;
-    int64_t* offsets = (int64_t*)(base + L.off_offsets);
+    BucketRec* recs = (BucketRec*)(base + L.off_recs);
     int64_t* nnz = (int64_t*)(base + L.off_nnz);
     int32_t* vals[2] = {(int32_t*)(base + L.off_vals[0]), (int32_t*)(base + L.off_vals[1])};
     void* keys[2] = {base + L.off_keys[0], base + L.off_keys[1]};
@@ -400,7 +618,7 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
             }
             ETB_LAUNCHED();
         }
-        // K4b: stable radix sort over the used key bits, then bucket heads
+        // K4b: stable radix sort over the used key bits, then one record per bucket head
         size_t temp_bytes = L.temp_bytes;
         void* temp = base + L.off_temp;
         cub::DoubleBuffer<int32_t> v(vals[0], vals[1]);
@@ -409,25 +627,24 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
             ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, L.n_total, 0, end_bit, stream));
             keys[0] = k.Current();
             temp_bytes = L.temp_bytes;
-            ETB_CUDA(cub::DeviceSelect::If(temp, temp_bytes, thrust::counting_iterator<int64_t>(0), offsets, nnz,
-                                           L.n_total, HeadPred32{(const uint32_t*)keys[0]}, stream));
+            ETB_CUDA(select_heads<uint32_t>(temp, temp_bytes, (const uint32_t*)keys[0], v.Current(), recs, nnz, L.n_total, stream));
         } else {
             cub::DoubleBuffer<uint64_t> k((uint64_t*)keys[0], (uint64_t*)keys[1]);
             ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, L.n_total, 0, end_bit, stream));
             keys[0] = k.Current();
             temp_bytes = L.temp_bytes;
-            ETB_CUDA(cub::DeviceSelect::If(temp, temp_bytes, thrust::counting_iterator<int64_t>(0), offsets, nnz,
-                                           L.n_total, HeadPred64{(const uint64_t*)keys[0]}, stream));
+            ETB_CUDA(select_heads<uint64_t>(temp, temp_bytes, (const uint64_t*)keys[0], v.Current(), recs, nnz, L.n_total, stream));
         }
         vals[0] = v.Current();
-        // CUB launches: histogram + one pass per 8 key bits (onesweep), select = 2 kernels
-        launch_counter() += 1 + (end_bit + 7) / 8 + 2;
+        // CUB launches: histogram + exclusive sum + one onesweep pass per 8 key bits; select = init + sweep
+        launch_counter() += 2 + (end_bit + 7) / 8 + 2;
     }
     if (view) {
         view->keys = keys[0];
         view->map = vals[0];
-        view->offsets = offsets;
+        view->records = recs;
         view->nnz = nnz;
+        view->scratch = base + L.off_counters;
         view->n_total = L.n_total;
         view->key_bytes = L.key_bytes;
         view->row_bits = L.row_bits;
@@ -442,10 +659,12 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
     ETB_REQUIRE(view, "etb_sgd_update: null index view");
     ETB_REQUIRE(n_items >= 0 && (n_items == 0 || items), "etb_sgd_update: bad items");
     if (n_items == 0 || view->n_total == 0) return ETB_OK;
+    IndexLayout L;  // the scratch region's layout is a pure function of the items
+    if (int32_t st = make_layout(items, n_items, L)) return st;
+    ETB_REQUIRE(L.n_total == view->n_total, "etb_sgd_update: items do not match the index view");
     std::vector<UpdClass> cls((size_t)n_items);
     for (int i = 0; i < n_items; ++i) {
         const etb_update_item& it = items[i];
-        if (int32_t st = validate_table(it.table, "etb_sgd_update")) return st;
         // update! on integer tables throws in the reference too (InexactError at
         // convert(eltype(table), opt.eta), src/sparseupdate.jl:173)
         ETB_REQUIRE(it.table.elt == ETB_F32 || it.table.elt == ETB_F64,
@@ -454,17 +673,23 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         ETB_REQUIRE(it.ld_delta >= it.table.dim, "etb_sgd_update: item %d: ld_delta < dim", i);
         cls[i] = classify_update(it);
     }
+    ETB_REQUIRE(view->num_splits >= 0 && (view->num_splits == 0 || (view->this_split >= 1 && view->this_split <= view->num_splits)),
+                "etb_sgd_update: bad IndexerView split %d of %d", view->this_split, view->num_splits);
     static thread_local UpdParams P;
-    P.keys = view->keys;
+    char* scratch = (char*)view->scratch;
+    P.recs = (const BucketRec*)view->records;
     P.map = view->map;
-    P.offsets = view->offsets;
     P.nnz = view->nnz;
+    P.counters = (LongCounters*)scratch;
+    P.longs = (LongRec*)(scratch + (L.off_long - L.off_counters));
+    P.chunks = (ChunkRec*)(scratch + (L.off_chunks - L.off_counters));
+    P.partials = scratch + (L.off_partials - L.off_counters);
+    P.partial_pitch = (int64_t)L.partial_pitch;
     P.n_total = view->n_total;
     P.eta = eta;
     P.row_bits = view->row_bits;
     P.fma = (flags & ETB_UPDATE_FMA) ? 1 : 0;
-    ETB_REQUIRE(view->num_splits >= 0 && (view->num_splits == 0 || (view->this_split >= 1 && view->this_split <= view->num_splits)),
-                "etb_sgd_update: bad IndexerView split %d of %d", view->this_split, view->num_splits);
+    P.split_long = (flags & ETB_UPDATE_SPLIT_LONG) ? 1 : 0;
     P.num_splits = view->num_splits;
     P.this_split = view->this_split;
     // one launch per run of consecutive items sharing a kernel class (all tables of a DLRM
@@ -484,17 +709,22 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         P.nslots = n;
         P.G = c.G;
         P.nvec = c.nvec;
+        if (P.split_long) ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
         const int64_t buckets_per_block = (kUThreads / 32) * 32;  // one 32-bucket tile per warp
-        const int64_t want = (view->n_total + buckets_per_block - 1) / buckets_per_block;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)kNumSMs * 16);  // grid-stride over bucket tiles
-        if (view->key_bytes == 4) {
-            if (c.elt == ETB_F32) launch_update_vb<float, uint32_t>(c, grid, stream, P);
-            else launch_update_vb<double, uint32_t>(c, grid, stream, P);
-        } else {
-            if (c.elt == ETB_F32) launch_update_vb<float, uint64_t>(c, grid, stream, P);
-            else launch_update_vb<double, uint64_t>(c, grid, stream, P);
-        }
+        const int grid = (int)((view->n_total + buckets_per_block - 1) / buckets_per_block);
+        launch_update(kKernelMain, c, grid, stream, P);
         ETB_LAUNCHED();
+        if (P.split_long && view->n_total > kLongThreshold) {
+            const int64_t max_chunks = view->n_total / kLongChunk + 1;
+            const int64_t per_block = kUThreads / c.G;
+            const int gridA = (int)std::min<int64_t>((max_chunks + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
+            launch_update(kKernelPartials, c, gridA, stream, P);
+            ETB_LAUNCHED();
+            const int64_t max_long = view->n_total / kLongThreshold + 1;
+            const int gridB = (int)std::min<int64_t>((max_long + per_block - 1) / per_block, (int64_t)kNumSMs * 4);
+            launch_update(kKernelCombine, c, gridB, stream, P);
+            ETB_LAUNCHED();
+        }
         i0 += n;
     }
     return ETB_OK;

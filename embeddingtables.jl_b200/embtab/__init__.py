@@ -10,6 +10,7 @@ from .lookup import (AbstractExecutionStrategy, ColumnWrap, DefaultStrategy, Pre
                      SimpleParallelStrategy, colwrap, destination, lookup, lookup_, maplookup, maplookup_)
 from .sparseupdate import (AbstractIndexer, DenseIndexer, Descent, Indexer, IndexerView, Slicer,
                            SparseEmbeddingUpdate, SparseIndexer, ensemble_update, index_, pullback, rrule,
+                           set_update_order,
                            uncompress, update_, update_table_)
 from .tables import (AbstractEmbeddingTable, ArgumentError, Dynamic, Forward, IndexingContext, NoContext,
                      SimpleEmbedding, SplitEmbedding, Static, Update, columnpointer, example, featuresize,

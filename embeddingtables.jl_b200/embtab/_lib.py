@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libembtab_b200.so")
+LIB_PATH = os.environ.get("ETB_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libembtab_b200.so")
 
 F32, F64, I32, I64 = 0, 1, 2, 3
 UPDATE_FMA, UPDATE_SPLIT_LONG = 1, 2
@@ -39,9 +39,10 @@ class UpdateItem(C.Structure):
 
 
 class IndexView(C.Structure):
-    _fields_ = [("keys", C.c_void_p), ("map", C.c_void_p), ("offsets", C.c_void_p),
-                ("nnz", C.c_void_p), ("n_total", C.c_int64), ("key_bytes", C.c_int32),
-                ("row_bits", C.c_int32), ("num_splits", C.c_int32), ("this_split", C.c_int32)]
+    _fields_ = [("keys", C.c_void_p), ("map", C.c_void_p), ("records", C.c_void_p),
+                ("nnz", C.c_void_p), ("scratch", C.c_void_p), ("n_total", C.c_int64),
+                ("key_bytes", C.c_int32), ("row_bits", C.c_int32), ("num_splits", C.c_int32),
+                ("this_split", C.c_int32)]
 
 
 _SIGS = {

@@ -92,14 +92,16 @@ class Indexer(AbstractIndexer):
         torch.cuda.current_stream().synchronize()
         nnz = int(_peek(v.nnz, 1, np.int64)[0])
         n = v.n_total
-        keys = _peek(v.keys, n, np.uint32 if v.key_bytes == 4 else np.uint64).astype(np.uint64)
         mp = _peek(v.map, n, np.int32)
-        offs = np.append(_peek(v.offsets, nnz, np.int64), n)
+        rec = _peek(v.records, nnz, np.dtype([("start", np.uint32), ("m0", np.int32), ("key", np.uint64)]))
+        offs = np.append(rec["start"].astype(np.int64), n)
         mask = np.uint64((1 << v.row_bits) - 1)
         out = {}
         for s in range(nnz):
-            k = keys[offs[s]]
-            out[(int(k >> np.uint64(v.row_bits)), int(k & mask) + 1)] = (mp[offs[s]:offs[s + 1]] + 1).tolist()
+            k = rec["key"][s]
+            members = (mp[offs[s]:offs[s + 1]] + 1).tolist()
+            assert members[0] == rec["m0"][s] + 1
+            out[(int(k >> np.uint64(v.row_bits)), int(k & mask) + 1)] = members
         return out
 
 
@@ -138,14 +140,30 @@ def index_(indexer: Indexer, tables, grads):
 
 
 # ------------------------------------------------------------------------------ update!
+# Reduction order of update!.  "strict": every bucket is accumulated strictly in occurrence order
+# like the reference (bit-identical to it).  "split": buckets with more than 128 members (hot
+# Zipf rows) are summed as 128-member chunks combined in chunk order -- deterministic and
+# atomics-free, but a different association (within the north star's 1e-5 tolerance); buckets of
+# up to 128 members are identical in both modes.
+_ORDER = {"mode": "split"}
+
+
+def set_update_order(mode: str):
+    """'split' (default) or 'strict' (bit-identical to the reference's sequential accumulation)."""
+    if mode not in ("split", "strict"):
+        raise ValueError(mode)
+    _ORDER["mode"] = mode
+
+
 def _flags(table) -> int:
     """The reference's @generated dispatch (src/sparseupdate.jl:131-154, src/simd.jl:5-12): the
     specialised FMA kernel for Static{N} Float32 tables with N*4 <= 512 and N % 16 == 0, the
     generic two-rounding kernel otherwise."""
     S = table.lookup_type
+    f = _lib.UPDATE_SPLIT_LONG if _ORDER["mode"] == "split" else 0
     if (isinstance(S, Static) and table.dtype == np.float32 and S.N * 4 <= 512 and S.N % 16 == 0):
-        return _lib.UPDATE_FMA
-    return 0
+        f |= _lib.UPDATE_FMA
+    return f
 
 
 def _apply(tables, grads, indexer, eta):

@@ -185,15 +185,22 @@ int32_t etb_last_launch_count(void);
  * reference src/utils.jl:527-532):
  *   keys[n_total]  sorted composite keys (table_slot << row_bits | row-1), uint32 or uint64
  *   map[n_total]   delta column (0-based) of each sorted position        (reference `map`)
- *   offsets[nnz]   start of each bucket in keys/map                      (reference `cumulative`)
- *   nnz            number of buckets (device int64; bucket s ends at offsets[s+1], or at
+ *   records[nnz]   one etb_bucket_record per bucket                      (reference `cumulative`)
+ *   nnz            number of buckets (device int64; bucket s ends at records[s+1].start, or at
  *                  n_total for the last one)
  */
+typedef struct etb_bucket_record {
+    uint32_t start; /* first sorted position of the bucket               */
+    int32_t m0;     /* delta column (0-based) of the bucket's first member */
+    uint64_t key;   /* table_slot << row_bits | row-1                      */
+} etb_bucket_record;
+
 typedef struct etb_index_view {
     const void* keys;       /* device */
     const int32_t* map;     /* device */
-    const int64_t* offsets; /* device */
+    const void* records;    /* device: etb_bucket_record[nnz] */
     const int64_t* nnz;     /* device */
+    void* scratch;          /* device: internal scratch of ETB_UPDATE_SPLIT_LONG */
     int64_t n_total;        /* sum of occurrences over items */
     int32_t key_bytes;      /* 4 or 8 */
     int32_t row_bits;       /* key = slot << row_bits | (row-1) */
