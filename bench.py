@@ -184,8 +184,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if world > 1:
-        from embtab import dist as ED  # table-wise sharded ensemble with all-to-all
-        return ED.bench_sharded(args, rank, world, local, globals())
+        return run_sharded(args, rank, world, local)
 
     lib = E.lib()
     rng = np.random.default_rng(SEED)
@@ -316,6 +315,126 @@ def run_ours(args):
         "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
     }
     print(json.dumps(line), flush=True)
+
+
+def run_sharded(args, rank, world, local):
+    """N > 1: table-wise sharding (north star / SURVEY 8e).  Weak scaling: every rank owns 26 tables
+    (26*N in the ensemble), the global batch stays 16384, every rank looks its tables up for the
+    whole global batch, the all-to-all gives each rank all 26*N tables for its 16384/N samples, the
+    reverse all-to-all carries the cotangent back and each owner updates its tables.  Per-GPU
+    lookup and update work equal the N=1 run's; value = all ranks' lookups / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+
+    import embtab as E
+    from embtab.dist import ShardedEnsemble, ShardPlan
+
+    lib = E.lib()
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
+    tables = []
+    for _ in range(NT):
+        buf = torch.rand(DIM * NROWS, device="cuda", dtype=torch.float32, generator=gen)
+        tables.append(E.SimpleEmbedding(E.DeviceArray(buf, (DIM, NROWS)), E.Static(DIM)))
+    plan = ShardPlan([DIM] * (NT * world), world, rank, PREPEND, BATCH)
+    ens = ShardedEnsemble(tables, plan)
+    I_host = make_indices(rng, args.dist, NT, NROWS, BAG, BATCH)
+    idx_pinned = E.pinned_empty((BAG, BATCH, NT), np.int64)
+    idx_pinned[...] = I_host
+    I_dev = E.DeviceArray.empty((BAG, BATCH, NT), np.int64).upload(idx_pinned)
+    out_shape = (plan.total_rows, plan.my_cols)
+    out_pinned = E.pinned_empty(out_shape, np.float32)
+    delta_pinned = E.pinned_empty(out_shape, np.float32)
+    delta_pinned.reshape(-1, order="F")[:] = rng.standard_normal(out_shape[0] * out_shape[1], dtype=np.float32)
+    delta_dev = E.DeviceArray.empty(out_shape, np.float32).upload(delta_pinned)
+    opt = E.Descent(ETA)
+    launches = [0]
+
+    def step(events=None):
+        ens.forward(I_dev)
+        n = ens.launches
+        if events: events[1].record()
+        grads = ens.backward(delta_dev)
+        n += 1
+        if events: events[2].record()
+        ens.update_(opt, grads)
+        n += lib.etb_last_launch_count() + 9   # update kernels + the index! launches (etb_index counted 9)
+        if events: events[3].record()
+        launches[0] = n
+
+    def step_e2e():
+        I_dev.upload(idx_pinned)
+        ens.forward(I_dev)
+        ens.out.download(out_pinned)
+        delta_dev.upload(delta_pinned)
+        ens.update_(opt, ens.backward(delta_dev))
+
+    def sync():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    end = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        sync()
+        for k in range(K):
+            ev[k][0].record()
+            step(ev[k])
+        end.record()
+        sync()
+    t = torch.tensor([ev[0][0].elapsed_time(end) / K,
+                      float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
+                      float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
+                      float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks, device-timed
+    ms_per_step, fwd_ms, bwd_ms, upd_ms = t.tolist()
+
+    for _ in range(2):
+        step_e2e()
+    sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        step_e2e()
+    e1.record()
+    sync()
+    e2e = torch.tensor([max(e0.elapsed_time(e1) / K, (time.perf_counter() - t0) * 1e3 / K)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_ms = e2e.item()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        lookups = world * NT * BATCH * BAG
+        s_, b_ = 4, 8
+        fwd_bytes = NT * BATCH * (BAG * (b_ + DIM * s_) + DIM * s_)
+        a2a_bytes = plan.my_rows * BATCH * s_ * (world - 1) / world          # sent per rank per direction
+        line = {
+            "metric": "embedding_lookups_per_sec", "value": lookups / (ms_per_step * 1e-3), "unit": "lookups/s",
+            "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD + f"; table-wise sharded: {NT} tables per GPU ({NT * world} total), global batch "
+                       f"{BATCH}, all-to-all fwd + reverse all-to-all bwd (NCCL)", "dist": args.dist, "index_type": "int64",
+                       "eta": ETA, "l2": "inputs larger than L2: 13.3 GB of tables per GPU, random rows; no flush needed"},
+            "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
+                    "d2h_bytes_per_step": int(out_pinned.nbytes)},
+            "gpu_launches": launches[0] * K, "clocks": clocks.result,
+            "roofline": {"bound": "hbm", "kernel": "pooled_kernel+a2a (fwd phase, max over ranks)",
+                         "achieved": fwd_bytes / fwd_ms / 1e6, "peak": peak, "unit": "GB/s",
+                         "frac": fwd_bytes / fwd_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src},
+            "phases_ms": {"fwd_lookup+a2a+unpack": fwd_ms, "bwd_pack+a2a": bwd_ms, "index+update": upd_ms},
+            "nvlink": {"bytes_sent_per_rank_per_direction": a2a_bytes, "peak_gbs": 770.0,
+                       "note": "phase times include the lookup / pack kernels; see profiles/ for the split"},
+            "cpu_baseline": None,
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def main():

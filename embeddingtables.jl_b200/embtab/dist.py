@@ -1,0 +1,171 @@
+"""Table-wise sharded ensembles over the GPUs of one NVSwitch box.
+
+The reference is single-process (no NCCL/MPI anywhere); this layer is the
+multi-GPU form the north star asks for: tables are block-partitioned over ranks (one process per
+GPU), every rank looks its tables up for the GLOBAL batch, and one all-to-all turns
+"all samples x my tables" into "my samples x all tables" -- the concatenated DLRM feature matrix
+of maplookup(PreallocationStrategy(prependrows), ...) for this rank's batch slice.  The backward
+pass is the reverse all-to-all of the cotangent's row blocks, after which each owner runs the
+ordinary ensemble update! on its tables.  Arithmetic per output column is exactly the 1-GPU
+path's, so results are bit-identical to it (only placement changes).
+
+Layout trick (K6): the lookup kernel writes straight into the all-to-all SEND layout (block p =
+my_rows x cols[p], dense; end to end the blocks are just the column-major my_rows x B_global
+matrix), so there is no pack pass in the forward; in the
+backward the RECEIVE buffer already is the (my_rows x global_batch) cotangent of my tables, so
+there is no unpack pass there.  The remaining strided copies (forward unpack, backward pack) are
+etb_a2a_unpack / etb_a2a_pack.
+
+ShardPlan and exchange() are pure host logic over torch tensors of any device; the CPU tests
+drive them with the gloo backend (tests/test_dist_cpu.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .darray import DeviceArray, as_device_indices, current_stream_ptr
+from .lookup import _item, _run
+from .sparseupdate import Indexer, SparseEmbeddingUpdate, update_
+from .tables import featuresize
+
+
+class ShardPlan:
+    """Who owns which tables, which rows of the feature matrix they fill, and which batch
+    columns each rank keeps.
+
+    dims          featuresize of every table of the GLOBAL ensemble, in ensemble order
+    world, rank   torch.distributed world
+    prependrows   PreallocationStrategy.prependrows of the feature matrix
+    batch_global  global batch (columns of the index arrays every owner receives)
+    """
+
+    def __init__(self, dims, world: int, rank: int, prependrows: int, batch_global: int):
+        self.dims = [int(d) for d in dims]
+        self.world, self.rank = int(world), int(rank)
+        self.prependrows, self.batch_global = int(prependrows), int(batch_global)
+        T = len(self.dims)
+        # block partition of tables: rank q owns tables [tlo[q], thi[q])
+        bounds = np.floor(np.arange(self.world + 1) * T / self.world + 0.5).astype(int)
+        self.tlo, self.thi = bounds[:-1].tolist(), bounds[1:].tolist()
+        self.rows = [sum(self.dims[a:b]) for a, b in zip(self.tlo, self.thi)]       # feature rows per owner
+        self.row_off = [self.prependrows + sum(self.rows[:q]) for q in range(self.world)]
+        self.total_rows = self.prependrows + sum(self.dims)
+        # block partition of the batch: rank p keeps columns [clo[p], chi[p])
+        cb = np.floor(np.arange(self.world + 1) * self.batch_global / self.world + 0.5).astype(int)
+        self.clo, self.chi = cb[:-1].tolist(), cb[1:].tolist()
+        self.cols = [b - a for a, b in zip(self.clo, self.chi)]
+
+    @property
+    def my_tables(self):
+        return range(self.tlo[self.rank], self.thi[self.rank])
+
+    @property
+    def my_rows(self):
+        return self.rows[self.rank]
+
+    @property
+    def my_cols(self):
+        return self.cols[self.rank]
+
+    # element counts of the all-to-all splits
+    def fwd_send_splits(self):   # to peer p: my tables' rows x p's columns
+        return [self.my_rows * c for c in self.cols]
+
+    def fwd_recv_splits(self):   # from owner q: q's rows x my columns
+        return [r * self.my_cols for r in self.rows]
+
+    def bwd_send_splits(self):
+        return self.fwd_recv_splits()
+
+    def bwd_recv_splits(self):
+        return self.fwd_send_splits()
+
+    def send_block_offset(self, p: int) -> int:
+        """element offset of peer p's block inside the forward send buffer"""
+        return self.my_rows * self.clo[p]
+
+    def recv_block_offset(self, q: int) -> int:
+        return self.my_cols * sum(self.rows[:q])
+
+
+def exchange(recv: torch.Tensor, send: torch.Tensor, recv_splits, send_splits, group=None):
+    """One all-to-all (NCCL on GPUs, gloo in the CPU tests)."""
+    dist.all_to_all_single(recv, send, list(recv_splits), list(send_splits), group=group)
+    return recv
+
+
+class ShardedEnsemble:
+    """This rank's tables of a table-wise sharded ensemble + the exchange buffers.
+
+    forward(I)       I = indices of MY tables for the GLOBAL batch (list of (bag, B_global) or
+                     (B_global,) arrays, or an N-d container) -> my slice of the feature matrix,
+                     (prependrows + sum(dims)) x my_cols; rows 1..prependrows are left untouched.
+    backward(delta)  delta = cotangent of that matrix -> SparseEmbeddingUpdates of my tables
+                     (delta views into the received (my_rows x B_global) buffer + global indices).
+    update_(opt, grads)
+    """
+
+    def __init__(self, tables_local, plan: ShardPlan, group=None):
+        self.tables, self.plan, self.group = list(tables_local), plan, group
+        assert len(self.tables) == len(plan.my_tables)
+        assert [featuresize(t) for t in self.tables] == [plan.dims[t] for t in plan.my_tables]
+        self.dtype = self.tables[0].dtype
+        p = plan
+        self.send = DeviceArray.empty((max(1, p.my_rows * p.batch_global),), self.dtype)
+        self.recv = DeviceArray.empty((max(1, (p.total_rows - p.prependrows) * p.my_cols),), self.dtype)
+        self.delta_global = DeviceArray.empty((max(1, p.my_rows), p.batch_global), self.dtype)
+        self.out = DeviceArray.empty((p.total_rows, p.my_cols), self.dtype)
+        self.indexer = Indexer()
+        self._I = None
+        self._rows = (C.c_int64 * p.world)(*p.rows)
+        self._row_off = (C.c_int64 * p.world)(*p.row_off)
+        self.launches = 0
+
+    def forward(self, I, out: DeviceArray = None) -> DeviceArray:
+        p = self.plan
+        Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else
+                                             [I.lastdim(t) for t in range(I.shape[-1])])]
+        self._I = Is
+        out = self.out if out is None else out
+        # Peer p's send block is (my_rows x cols[p]) dense at element offset my_rows*clo[p]: the
+        # blocks laid end to end ARE the column-major (my_rows x B_global) matrix of my tables'
+        # lookups, so one item per table writes the whole send layout.
+        send = DeviceArray(self.send.buf, (p.my_rows, p.batch_global), 0, p.my_rows, self.dtype)
+        items, off = [], 0
+        for t, i in zip(self.tables, Is):
+            f = featuresize(t)
+            if p.batch_global > 0:
+                items.append(_item(t, i, send.rows(off, off + f)))
+            off += f
+        if items:
+            _run(items)                                        # K6: lookups written in send layout
+            self.launches = _lib.lib().etb_last_launch_count()
+        n_send, n_recv = p.my_rows * p.batch_global, (p.total_rows - p.prependrows) * p.my_cols
+        exchange(self.recv.buf[:n_recv], self.send.buf[:n_send], p.fwd_recv_splits(), p.fwd_send_splits(), self.group)
+        _lib.check(_lib.lib().etb_a2a_unpack(out.ptr, out.ld, self.recv.ptr, self._rows, self._row_off, p.world,
+                                             p.my_cols, out.elt, C.c_void_p(current_stream_ptr())))
+        self.launches += 1
+        return out
+
+    def backward(self, delta: DeviceArray):
+        p = self.plan
+        n_send, n_recv = (p.total_rows - p.prependrows) * p.my_cols, p.my_rows * p.batch_global
+        # pack my cotangent's row blocks by owner (reuses the forward receive buffer)
+        _lib.check(_lib.lib().etb_a2a_pack(self.recv.ptr, delta.ptr, delta.ld, self._rows, self._row_off, p.world,
+                                           p.my_cols, delta.elt, C.c_void_p(current_stream_ptr())))
+        exchange(self.delta_global.buf[:n_recv], self.recv.buf[:n_send], p.bwd_recv_splits(), p.bwd_send_splits(),
+                 self.group)
+        grads, off = [], 0
+        for t, i in zip(self.tables, self._I):
+            f = featuresize(t)
+            grads.append(SparseEmbeddingUpdate(t.lookup_type, self.delta_global.rows(off, off + f), i))
+            off += f
+        return grads
+
+    def update_(self, opt, grads):
+        update_(opt, self.tables, grads, [self.indexer])
