@@ -337,7 +337,7 @@ def run_sharded(args, rank, world, local):
         buf = torch.rand(DIM * NROWS, device="cuda", dtype=torch.float32, generator=gen)
         tables.append(E.SimpleEmbedding(E.DeviceArray(buf, (DIM, NROWS)), E.Static(DIM)))
     plan = ShardPlan([DIM] * (NT * world), world, rank, PREPEND, BATCH)
-    ens = ShardedEnsemble(tables, plan)
+    ens = ShardedEnsemble(tables, plan, fused=not args.nccl_a2a)
     I_host = make_indices(rng, args.dist, NT, NROWS, BAG, BATCH)
     idx_pinned = E.pinned_empty((BAG, BATCH, NT), np.int64)
     idx_pinned[...] = I_host
@@ -419,7 +419,9 @@ def run_sharded(args, rank, world, local):
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD + f"; table-wise sharded: {NT} tables per GPU ({NT * world} total), global batch "
-                       f"{BATCH}, all-to-all fwd + reverse all-to-all bwd (NCCL)", "dist": args.dist, "index_type": "int64",
+                       f"{BATCH}, exchange = " + ("NCCL all-to-all + pack/unpack" if args.nccl_a2a else
+                       "fused: lookup/scatter kernels store into peer HBM over NVLink (CUDA IPC), all-reduce barrier"),
+                       "dist": args.dist, "index_type": "int64",
                        "eta": ETA, "l2": "inputs larger than L2: 13.3 GB of tables per GPU, random rows; no flush needed"},
             "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
@@ -428,7 +430,7 @@ def run_sharded(args, rank, world, local):
             "roofline": {"bound": "hbm", "kernel": "pooled_kernel+a2a (fwd phase, max over ranks)",
                          "achieved": fwd_bytes / fwd_ms / 1e6, "peak": peak, "unit": "GB/s",
                          "frac": fwd_bytes / fwd_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src},
-            "phases_ms": {"fwd_lookup+a2a+unpack": fwd_ms, "bwd_pack+a2a": bwd_ms, "index+update": upd_ms},
+            "phases_ms": {"fwd_lookup+exchange": fwd_ms, "bwd_exchange": bwd_ms, "index+update": upd_ms},
             "nvlink": {"bytes_sent_per_rank_per_direction": a2a_bytes, "peak_gbs": 770.0,
                        "note": "phase times include the lookup / pack kernels; see profiles/ for the split"},
             "cpu_baseline": None,
@@ -445,6 +447,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dist", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-a2a", action="store_true",
+                    help="N>1: exchange with NCCL all-to-all + pack/unpack instead of fused NVLink peer stores")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

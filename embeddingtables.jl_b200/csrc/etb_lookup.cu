@@ -30,7 +30,7 @@
 namespace etb {
 
 constexpr int kThreads = 256;
-constexpr int kMaxItems = 96;    // descriptors per launch (kernel-parameter space: 96*72 B)
+constexpr int kMaxItems = 256;   // descriptors per launch (kernel-parameter space: 256*72 B = 18 KB of 32 KB)
 constexpr int kGatherCols = 4;   // columns per group in the gather kernel (loads in flight)
 
 struct LookupDesc {  // 72 bytes

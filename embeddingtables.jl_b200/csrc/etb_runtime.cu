@@ -123,6 +123,28 @@ int32_t etb_memset(void* dst, int32_t byte, size_t bytes, void* stream) {
     return ETB_OK;
 }
 
+int32_t etb_ipc_export(void* ptr, void* handle_host) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == ETB_IPC_HANDLE_BYTES, "IPC handle size");
+    ETB_REQUIRE(ptr && handle_host, "etb_ipc_export: null pointer");
+    cudaIpcMemHandle_t h;
+    ETB_CUDA(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_host, &h, sizeof(h));
+    return ETB_OK;
+}
+
+int32_t etb_ipc_import(const void* handle_host, void** ptr_host) {
+    ETB_REQUIRE(handle_host && ptr_host, "etb_ipc_import: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    ETB_CUDA(cudaIpcOpenMemHandle(ptr_host, h, cudaIpcMemLazyEnablePeerAccess));
+    return ETB_OK;
+}
+
+int32_t etb_ipc_close(void* ptr) {
+    if (ptr) ETB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return ETB_OK;
+}
+
 int32_t etb_stream_create(void** stream_host) {
     ETB_REQUIRE(stream_host, "etb_stream_create: null output");
     cudaStream_t s;

@@ -752,18 +752,17 @@ __global__ void uncompress_kernel(T* dst, int64_t ld_dst, int dim, const T* delt
 struct A2ABlocks {
     int64_t rows[16];
     int64_t row_off[16];
-    int64_t buf_off[16];  // element offset of block r in the dense buffer
+    char* dense[16];  // block r's dense (rows[r] x batch_local) matrix: local buffer or peer memory
 };
 
 template <int VB, bool UNPACK>
 __global__ void __launch_bounds__(256)
-a2a_copy_kernel(char* strided, int64_t ld_bytes, char* dense, const __grid_constant__ A2ABlocks B, int64_t batch_local,
-                int es) {
+a2a_copy_kernel(char* strided, int64_t ld_bytes, const __grid_constant__ A2ABlocks B, int64_t batch_local, int es) {
     const int r = blockIdx.y;
     const int64_t row_bytes = B.rows[r] * es;
     const int64_t vec_per_col = row_bytes / VB;
     const int64_t total = vec_per_col * batch_local;
-    char* dbase = dense + B.buf_off[r] * es;
+    char* dbase = B.dense[r];
     char* sbase = strided + B.row_off[r] * es;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t col = t / vec_per_col, v = t - col * vec_per_col;
@@ -775,12 +774,13 @@ a2a_copy_kernel(char* strided, int64_t ld_bytes, char* dense, const __grid_const
     }
 }
 
-static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, const int64_t* rows, const int64_t* row_off,
-                        int32_t nranks, int64_t batch_local, int32_t elt, cudaStream_t stream) {
+// dense == nullptr: per-block destinations in dense_ptrs (peer memory); else blocks laid end to end in `dense`
+static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, void* const* dense_ptrs, const int64_t* rows,
+                        const int64_t* row_off, int32_t nranks, int64_t batch_local, int32_t elt, cudaStream_t stream) {
     launch_counter() = 0;
     ETB_REQUIRE(nranks >= 1 && nranks <= 16, "etb_a2a: nranks must be in 1..16");
     ETB_REQUIRE(elt_valid(elt), "etb_a2a: bad element type");
-    ETB_REQUIRE(strided && dense && rows && row_off, "etb_a2a: null pointer");
+    ETB_REQUIRE(strided && (dense || dense_ptrs) && rows && row_off, "etb_a2a: null pointer");
     if (batch_local == 0) return ETB_OK;
     const int es = (int)elt_bytes(elt);
     A2ABlocks B;
@@ -789,20 +789,21 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, con
     for (int r = 0; r < nranks; ++r) {
         B.rows[r] = rows[r];
         B.row_off[r] = row_off[r];
-        B.buf_off[r] = off;
+        B.dense[r] = dense ? (char*)dense + off * es : (char*)dense_ptrs[r];
+        ETB_REQUIRE(B.dense[r] || rows[r] == 0, "etb_a2a: null block pointer");
         off += rows[r] * batch_local;
         max_rows = std::max(max_rows, rows[r]);
-        while (vb > es && ((rows[r] * es) % vb || (row_off[r] * es) % vb || (B.buf_off[r] * es) % vb)) vb >>= 1;
+        while (vb > es && ((rows[r] * es) % vb || (row_off[r] * es) % vb || (uintptr_t)B.dense[r] % vb)) vb >>= 1;
     }
-    while (vb > es && ((ld * es) % vb || (uintptr_t)strided % vb || (uintptr_t)dense % vb)) vb >>= 1;
+    while (vb > es && ((ld * es) % vb || (uintptr_t)strided % vb)) vb >>= 1;
     if (vb < 4) vb = 4;
     if (max_rows == 0) return ETB_OK;
     const int64_t total = max_rows * es / vb * batch_local;
     dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8), (unsigned)nranks);
     const int64_t ldb = ld * es;
 #define ETB_A2A(VBV)                                                                                          \
-    if (unpack) a2a_copy_kernel<VBV, true><<<grid, 256, 0, stream>>>((char*)strided, ldb, (char*)dense, B, batch_local, es); \
-    else a2a_copy_kernel<VBV, false><<<grid, 256, 0, stream>>>((char*)strided, ldb, (char*)dense, B, batch_local, es);
+    if (unpack) a2a_copy_kernel<VBV, true><<<grid, 256, 0, stream>>>((char*)strided, ldb, B, batch_local, es); \
+    else a2a_copy_kernel<VBV, false><<<grid, 256, 0, stream>>>((char*)strided, ldb, B, batch_local, es);
     if (vb == 16) { ETB_A2A(16) } else if (vb == 8) { ETB_A2A(8) } else { ETB_A2A(4) }
 #undef ETB_A2A
     ETB_LAUNCHED();
@@ -866,14 +867,20 @@ int32_t etb_uncompress(void* dst, int64_t ld_dst, int32_t dim, int32_t elt, cons
 
 int32_t etb_a2a_unpack(void* dst, int64_t ld_dst, const void* recv, const int64_t* rows_host, const int64_t* row_off_host,
                        int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
-    return a2a_copy(true, dst, ld_dst, const_cast<void*>(recv), rows_host, row_off_host, nranks, batch_local, elt,
-                    (cudaStream_t)stream);
+    return a2a_copy(true, dst, ld_dst, const_cast<void*>(recv), nullptr, rows_host, row_off_host, nranks, batch_local,
+                    elt, (cudaStream_t)stream);
 }
 
 int32_t etb_a2a_pack(void* send, const void* src, int64_t ld_src, const int64_t* rows_host, const int64_t* row_off_host,
                      int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
-    return a2a_copy(false, const_cast<void*>(src), ld_src, send, rows_host, row_off_host, nranks, batch_local, elt,
-                    (cudaStream_t)stream);
+    return a2a_copy(false, const_cast<void*>(src), ld_src, send, nullptr, rows_host, row_off_host, nranks, batch_local,
+                    elt, (cudaStream_t)stream);
+}
+
+int32_t etb_a2a_scatter(void* const* dst_ptrs_host, const void* src, int64_t ld_src, const int64_t* rows_host,
+                        const int64_t* row_off_host, int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
+    return a2a_copy(false, const_cast<void*>(src), ld_src, nullptr, dst_ptrs_host, rows_host, row_off_host, nranks,
+                    batch_local, elt, (cudaStream_t)stream);
 }
 
 }  // extern "C"

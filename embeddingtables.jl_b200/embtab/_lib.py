@@ -78,6 +78,11 @@ _SIGS = {
                         C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p], C.c_int32),
     "etb_a2a_unpack": ([C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                         C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
+    "etb_ipc_export": ([C.c_void_p, C.c_void_p], C.c_int32),
+    "etb_ipc_import": ([C.c_void_p, C.POINTER(C.c_void_p)], C.c_int32),
+    "etb_ipc_close": ([C.c_void_p], C.c_int32),
+    "etb_a2a_scatter": ([C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                         C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
     "etb_a2a_pack": ([C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                       C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
 }

@@ -64,6 +64,22 @@ class DeviceArray:
         buf = torch.from_numpy(flat).to(device or "cuda")
         return DeviceArray(buf, a.shape, dtype=a.dtype)
 
+    @staticmethod
+    def from_pointer(ptr: int, shape, dtype=np.float32, ld=None) -> "DeviceArray":
+        """Wrap raw device memory (e.g. an etb_malloc allocation or a peer's IPC-mapped buffer).
+        No ownership: the caller keeps the allocation alive."""
+        shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        ld_ = int(ld) if ld is not None else shape[0]
+        n = (shape[-1] - 1) * ld_ + shape[0] if len(shape) == 2 else int(np.prod(shape))
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (max(n, 1),), "typestr": np.dtype(dtype).str,
+                                        "data": (int(ptr), False), "version": 3}
+        buf = torch.as_tensor(raw, device="cuda")
+        return DeviceArray(buf, shape, 0, ld_, dtype)
+
     def similar(self, dtype=None, shape=None) -> "DeviceArray":
         """Julia `similar(example(A), T, dims)` (reference src/lookup.jl:20-22)."""
         return DeviceArray.empty(self.shape if shape is None else shape, dtype or self.dtype,

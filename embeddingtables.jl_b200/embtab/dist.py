@@ -110,9 +110,15 @@ class ShardedEnsemble:
     update_(opt, grads)
     """
 
-    def __init__(self, tables_local, plan: ShardPlan, group=None):
-        self.tables, self.plan, self.group = list(tables_local), plan, group
+    def __init__(self, tables_local, plan: ShardPlan, group=None, fused: bool = False):
+        """fused=False: NCCL all-to-all + pack/unpack kernels.  fused=True: the lookup kernel stores
+        straight into the peers' feature matrices and the backward scatter straight into the owners'
+        cotangent buffers over NVLink (CUDA-IPC mapped peer memory); the only collective left is a
+        one-element all-reduce used as a stream-ordered barrier."""
+        self.tables, self.plan, self.group, self.fused = list(tables_local), plan, group, bool(fused)
         assert len(self.tables) == len(plan.my_tables)
+        if not self.tables:
+            raise ValueError("every rank must own at least one table (fewer tables than ranks)")
         assert [featuresize(t) for t in self.tables] == [plan.dims[t] for t in plan.my_tables]
         self.dtype = self.tables[0].dtype
         p = plan
@@ -125,12 +131,94 @@ class ShardedEnsemble:
         self._rows = (C.c_int64 * p.world)(*p.rows)
         self._row_off = (C.c_int64 * p.world)(*p.row_off)
         self.launches = 0
+        if self.fused:
+            self._setup_peer_memory()
+
+    # ---- fused mode: peer-mapped buffers -------------------------------------------------
+    def _setup_peer_memory(self):
+        p, lib, es = self.plan, _lib.lib(), np.dtype(self.dtype).itemsize
+        max_cols = max(p.cols)
+        sizes = [p.total_rows * max_cols * es, max(1, p.my_rows) * p.batch_global * es]
+        self._raw = []
+        for nbytes in sizes:                               # raw cudaMalloc: an IPC handle maps a whole allocation
+            ptr = C.c_void_p()
+            _lib.check(lib.etb_malloc(C.byref(ptr), max(nbytes, 256)))
+            self._raw.append(ptr.value)
+        handles = np.zeros(2 * 64, np.uint8)
+        for k, ptr in enumerate(self._raw):
+            _lib.check(lib.etb_ipc_export(ptr, handles[64 * k:].ctypes.data))
+        mine = torch.from_numpy(handles).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(p.world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        self._peer_out, self._peer_dglob, self._imported = [], [], []
+        for q in range(p.world):
+            if q == p.rank:
+                self._peer_out.append(self._raw[0]); self._peer_dglob.append(self._raw[1])
+                continue
+            h = gathered[q].cpu().numpy()
+            ptrs = []
+            for k in range(2):
+                ptr = C.c_void_p()
+                _lib.check(lib.etb_ipc_import(np.ascontiguousarray(h[64 * k:64 * k + 64]).ctypes.data, C.byref(ptr)))
+                ptrs.append(ptr.value)
+                self._imported.append(ptr.value)
+            self._peer_out.append(ptrs[0]); self._peer_dglob.append(ptrs[1])
+        # my own buffers, as DeviceArrays over the raw allocations
+        self.out = DeviceArray.from_pointer(self._raw[0], (p.total_rows, p.my_cols), self.dtype)
+        self.delta_global = DeviceArray.from_pointer(self._raw[1], (max(1, p.my_rows), p.batch_global), self.dtype)
+        self._peer_out_arrays = [DeviceArray.from_pointer(self._peer_out[q], (p.total_rows, p.cols[q]), self.dtype)
+                                 for q in range(p.world)]
+        self._flag = torch.zeros(1, device="cuda")
+        # owner q's cotangent buffer is rows[q] x B_global; my columns start at clo[rank]
+        self._scatter_ptrs = (C.c_void_p * p.world)(*[self._peer_dglob[q] + p.clo[p.rank] * p.rows[q] * es
+                                                      for q in range(p.world)])
+        dist.barrier(group=self.group)
+
+    def _barrier(self):
+        """stream-ordered barrier: completes on this rank's stream only after every rank's preceding
+        kernels (whose completion makes their peer stores visible) have finished."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def close(self):
+        if self.fused:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+            for ptr in self._imported:
+                _lib.lib().etb_ipc_close(ptr)
+            for ptr in self._raw:
+                _lib.lib().etb_free(ptr)
+            self._imported, self._raw, self.fused = [], [], False
+
+    def _forward_fused(self, Is):
+        p = self.plan
+        items, off = [], 0
+        for t, i in zip(self.tables, Is):
+            f = featuresize(t)
+            for q in range(p.world):                      # my rows of peer q's feature matrix, q's columns
+                if p.cols[q]:
+                    dst = self._peer_out_arrays[q].rows(p.row_off[p.rank] + off, p.row_off[p.rank] + off + f)
+                    items.append(_item(t, i.cols(p.clo[q], p.chi[q]), dst))
+            off += f
+        if items:
+            _run(items)
+            self.launches = _lib.lib().etb_last_launch_count()
+        self._barrier()
+        return self.out
+
+    def _backward_fused(self, delta: DeviceArray):
+        p = self.plan
+        _lib.check(_lib.lib().etb_a2a_scatter(self._scatter_ptrs, delta.ptr, delta.ld, self._rows, self._row_off, p.world,
+                                              p.my_cols, delta.elt, C.c_void_p(current_stream_ptr())))
+        self._barrier()
 
     def forward(self, I, out: DeviceArray = None) -> DeviceArray:
         p = self.plan
         Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else
                                              [I.lastdim(t) for t in range(I.shape[-1])])]
         self._I = Is
+        if self.fused:
+            assert out is None, "fused mode writes into the peer-mapped self.out"
+            return self._forward_fused(Is)
         out = self.out if out is None else out
         # Peer p's send block is (my_rows x cols[p]) dense at element offset my_rows*clo[p]: the
         # blocks laid end to end ARE the column-major (my_rows x B_global) matrix of my tables'
@@ -154,12 +242,18 @@ class ShardedEnsemble:
 
     def backward(self, delta: DeviceArray):
         p = self.plan
+        if self.fused:
+            self._backward_fused(delta)
+            return self._grads()
         n_send, n_recv = (p.total_rows - p.prependrows) * p.my_cols, p.my_rows * p.batch_global
         # pack my cotangent's row blocks by owner (reuses the forward receive buffer)
         _lib.check(_lib.lib().etb_a2a_pack(self.recv.ptr, delta.ptr, delta.ld, self._rows, self._row_off, p.world,
                                            p.my_cols, delta.elt, C.c_void_p(current_stream_ptr())))
         exchange(self.delta_global.buf[:n_recv], self.recv.buf[:n_send], p.bwd_recv_splits(), p.bwd_send_splits(),
                  self.group)
+        return self._grads()
+
+    def _grads(self):
         grads, off = [], 0
         for t, i in zip(self.tables, self._I):
             f = featuresize(t)

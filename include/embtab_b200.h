@@ -255,6 +255,25 @@ int32_t etb_a2a_pack(void* send, const void* src, int64_t ld_src, const int64_t*
                      const int64_t* row_off_host, int32_t nranks, int64_t batch_local, int32_t elt,
                      void* stream);
 
+/* Fused exchange over NVLink peer memory (one process per GPU, buffers shared with CUDA IPC).
+ * etb_ipc_export/import/close wrap cudaIpcGetMemHandle / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle
+ * for buffers allocated with etb_malloc; `handle_host` is ETB_IPC_HANDLE_BYTES bytes of host memory
+ * that the host layer ships to the peers (torch.distributed all_gather).
+ *
+ * With peer-mapped destinations the forward needs no collective at all: etb_maplookup's `dst`
+ * pointers are simply addresses inside the PEERS' feature matrices.  etb_a2a_scatter is the backward
+ * counterpart: row block r of `src` (rows_host[r] x batch_local at row row_off_host[r]) is stored as a
+ * dense rows_host[r] x batch_local matrix at dst_ptrs_host[r] -- a peer address inside owner r's
+ * (rows_r x B_global) cotangent buffer.  The caller orders the stores against the consumers with a
+ * stream-ordered barrier (kernel completion makes peer stores visible system-wide). */
+#define ETB_IPC_HANDLE_BYTES 64
+int32_t etb_ipc_export(void* ptr, void* handle_host);
+int32_t etb_ipc_import(const void* handle_host, void** ptr_host);
+int32_t etb_ipc_close(void* ptr);
+int32_t etb_a2a_scatter(void* const* dst_ptrs_host, const void* src, int64_t ld_src,
+                        const int64_t* rows_host, const int64_t* row_off_host, int32_t nranks,
+                        int64_t batch_local, int32_t elt, void* stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -17,7 +17,7 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rng = np.random.default_rng(7)                      # same data on every rank
-dims = [128, 128, 64, 128, 16, 128]
+dims = [128, 128, 64, 128, 16, 128, 32, 128, 128, 64]   # >= 8 tables so that every rank of an 8-GPU box owns one
 nrows, bag, batch, prepend = 777, 5, 203, 16
 base = [rng.standard_normal((d, nrows)).astype(np.float32) for d in dims]
 I = [rng.integers(1, nrows + 1, (bag, batch)) for _ in dims]
@@ -31,20 +31,26 @@ E.update_(E.Descent(0.1), ref_tables, back(delta)[2], [E.Indexer()])
 
 plan = ShardPlan(dims, world, rank, prepend, batch)
 mine = list(plan.my_tables)
-ens = ShardedEnsemble([E.SimpleEmbedding(base[t].copy()) for t in mine], plan)
-ens.out.fill(-5.0)
-out = ens.forward([I[t] for t in mine])
-got = out.numpy()
-want = ref_out.numpy()[:, plan.clo[rank]:plan.chi[rank]]
-assert np.array_equal(got[prepend:], want[prepend:]), "sharded forward differs"
-assert np.all(got[:prepend] == -5.0), "prepend rows were touched"
-d_local = E.DeviceArray.from_numpy(delta[:, plan.clo[rank]:plan.chi[rank]])
-grads = ens.backward(d_local)
-ens.update_(E.Descent(0.1), grads)
-for t, tab in zip(mine, ens.tables):
-    assert np.array_equal(tab.to_numpy(), ref_tables[t].to_numpy()), f"table {t} differs after update"
-torch.cuda.synchronize()
-dist.barrier()
+for fused in (False, True):     # NCCL all-to-all + pack/unpack, then NVLink peer stores
+    ens = ShardedEnsemble([E.SimpleEmbedding(base[t].copy()) for t in mine], plan, fused=fused)
+    ens.out.fill(-5.0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    for rep in range(2):        # twice: buffers are reused across steps
+        out = ens.forward([I[t] for t in mine])
+        got = out.numpy()
+        want = ref_out.numpy()[:, plan.clo[rank]:plan.chi[rank]]
+        assert np.array_equal(got[prepend:], want[prepend:]), f"sharded forward differs (fused={fused})"
+        assert np.all(got[:prepend] == -5.0), "prepend rows were touched"
+        d_local = E.DeviceArray.from_numpy(delta[:, plan.clo[rank]:plan.chi[rank]])
+        grads = ens.backward(d_local)
+        if rep == 1:            # update once, after the second (buffer-reusing) round trip
+            ens.update_(E.Descent(0.1), grads)
+    for t, tab in zip(mine, ens.tables):
+        assert np.array_equal(tab.to_numpy(), ref_tables[t].to_numpy()), f"table {t} differs after update (fused={fused})"
+    torch.cuda.synchronize()
+    dist.barrier()
+    ens.close()
 if rank == 0:
     print("dist check ok", world)
 dist.destroy_process_group()
