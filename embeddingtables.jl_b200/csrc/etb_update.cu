@@ -51,19 +51,24 @@ struct alignas(16) BucketRec {
     uint64_t key;    // slot << row_bits | (row - 1)
 };
 
-// long-bucket bookkeeping of ETB_UPDATE_SPLIT_LONG
+// Bucket classes of the update: SHORT (<= kShortMax members) finish inside the main kernel; MEDIUM
+// (kShortMax < members <= kLongThreshold, and every larger bucket in strict mode) go to a worklist
+// and are reduced strictly in order by medium_buckets_kernel with 8 rows in flight; LONG
+// (> kLongThreshold, ETB_UPDATE_SPLIT_LONG only) are reduced as kLongChunk-member chunks combined in
+// chunk order.
+constexpr int kShortMax = 4;
 constexpr int kLongThreshold = 128;  // buckets with more members than this are "long"
 constexpr int kLongChunk = 128;      // members per partial sum
-struct LongCounters { uint32_t n_long, n_chunks; };
+struct LongCounters { uint32_t n_long, n_chunks, n_medium, pad; };
 struct LongRec { uint32_t bucket, chunk_base, nchunks, pad; };
 struct ChunkRec { uint32_t long_id, chunk; };
 
 struct IndexLayout {
     int64_t n_total;
     int32_t row_bits, slot_bits, key_bytes;
-    size_t max_long, max_chunks, partial_pitch;
-    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_counters, off_long, off_chunks, off_partials, off_temp,
-        temp_bytes, total;
+    size_t max_long, max_chunks, max_medium, partial_pitch;
+    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_counters, off_long, off_chunks, off_medium, off_partials,
+        off_temp, temp_bytes, total;
 };
 
 static int bits_for(uint64_t count) {  // bits needed to represent 0 .. count-1
@@ -126,6 +131,7 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     const size_t n = (size_t)std::max<int64_t>(n_total, 1);
     L.max_long = n / kLongThreshold + 1;
     L.max_chunks = n / kLongChunk + L.max_long;
+    L.max_medium = n / (kShortMax + 1) + 1;
     L.partial_pitch = align_up(max_row_bytes, 16);
     size_t off = 0;
     for (int b = 0; b < 2; ++b) { L.off_keys[b] = off; off = align_up(off + n * L.key_bytes); }
@@ -135,6 +141,7 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     L.off_counters = off; off = align_up(off + sizeof(LongCounters));
     L.off_long = off; off = align_up(off + L.max_long * sizeof(LongRec));
     L.off_chunks = off; off = align_up(off + L.max_chunks * sizeof(ChunkRec));
+    L.off_medium = off; off = align_up(off + L.max_medium * sizeof(uint32_t));
     L.off_partials = off; off = align_up(off + L.max_chunks * L.partial_pitch);
     // CUB temp storage: max over the sort and the select
     size_t t_sort = 0, t_sel = 0;
@@ -202,6 +209,7 @@ struct UpdParams {
     LongCounters* counters;
     LongRec* longs;
     ChunkRec* chunks;
+    uint32_t* mediums;
     char* partials;
     int64_t partial_pitch;
     int64_t n_total;
@@ -339,8 +347,9 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         const bool mine = valid && slot >= 0 && slot < P.nslots;  // else another launch's class
         const UpdDesc& md = P.item[mine ? slot : 0];
         int cnt = mine ? (int)(stop - start) : 0;
-        if (P.split_long && cnt > kLongThreshold) {
-            register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+        if (cnt > kShortMax) {
+            if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            else P.mediums[atomicAdd(&P.counters->n_medium, 1u)] = (uint32_t)s;
             cnt = 0;
         }
         TileMeta m;
@@ -380,7 +389,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                         for (int p = 0; p < VPL; ++p)
 #pragma unroll
                             for (int e = 0; e < V::NE; ++e) acc[p].e[e] = T(0) + v0[u][p].e[e];
-                        if (m2.cnt > 1)  // duplicates: the rest of the bucket, strictly in order
+                        if (m2.cnt > 1)  // a few duplicates (<= kShortMax members): the rest, strictly in order
                             accumulate_members<T, VB, VPL, U>(acc, P.item[m2.slot], P.map, (int64_t)m2.start + 1,
                                                               (int64_t)m2.start + m2.cnt, vi, G, gl, lane, gmask);
                         char* row = const_cast<char*>(s_meta[gbase + k0 + u].row);
@@ -395,6 +404,54 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                             }
                         }
                     }
+                }
+            }
+        }
+    }
+}
+
+// MEDIUM buckets: one group per bucket, accumulated from zero strictly in occurrence order with 8
+// rows in flight -- the reference's order exactly, just with the loads issued ahead of the adds.
+template <typename T, int VB, int VPL>
+__global__ void __launch_bounds__(kUThreads)
+medium_buckets_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+    using V = Vec<T, VB>;
+    const int G = P.G, nvec = P.nvec;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (G - 1);
+    const unsigned gmask = group_mask(G, lane);
+    const uint32_t n_medium = P.counters->n_medium;
+    const int64_t nnz = *P.nnz;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    const T eta = (T)P.eta;
+    const bool fma = P.fma != 0;
+    const uint32_t groups_total = gridDim.x * (kUThreads / G);
+    for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_medium; i += groups_total) {
+        const uint32_t b = P.mediums[i];
+        const BucketRec rec = P.recs[b];
+        const int64_t stop = ((int64_t)b + 1 < nnz) ? (int64_t)P.recs[b + 1].start : P.n_total;
+        const UpdDesc& d = P.item[(int)(rec.key >> P.row_bits) - P.slot0];
+        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
+        for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
+            int vi[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
+            V old[VPL], acc[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) {
+                ld_plain<VB>(&old[p], row + vi[p]);
+#pragma unroll
+                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
+            }
+            accumulate_members<T, VB, VPL, U>(acc, d, P.map, (int64_t)rec.start, stop, vi, G, gl, lane, gmask);
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) {
+                if (pass0 + gl + p * G < nvec) {
+                    V out;
+#pragma unroll
+                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, fma);
+                    st_plain<VB>(row + vi[p], &out);
                 }
             }
         }
@@ -532,11 +589,12 @@ static UpdClass classify_update(const etb_update_item& it) {
     return c;
 }
 
-enum { kKernelMain = 0, kKernelPartials = 1, kKernelCombine = 2 };
+enum { kKernelMain = 0, kKernelPartials = 1, kKernelCombine = 2, kKernelMedium = 3 };
 
 template <typename T, int VB, int VPL>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain) sgd_update_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
+    else if (which == kKernelMedium) medium_buckets_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
     else if (which == kKernelPartials) long_partials_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
     else long_combine_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
 }
@@ -683,6 +741,7 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
     P.counters = (LongCounters*)scratch;
     P.longs = (LongRec*)(scratch + (L.off_long - L.off_counters));
     P.chunks = (ChunkRec*)(scratch + (L.off_chunks - L.off_counters));
+    P.mediums = (uint32_t*)(scratch + (L.off_medium - L.off_counters));
     P.partials = scratch + (L.off_partials - L.off_counters);
     P.partial_pitch = (int64_t)L.partial_pitch;
     P.n_total = view->n_total;
@@ -709,14 +768,20 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         P.nslots = n;
         P.G = c.G;
         P.nvec = c.nvec;
-        if (P.split_long) ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
+        ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
         const int64_t buckets_per_block = (kUThreads / 32) * 32;  // one 32-bucket tile per warp
         const int grid = (int)((view->n_total + buckets_per_block - 1) / buckets_per_block);
         launch_update(kKernelMain, c, grid, stream, P);
         ETB_LAUNCHED();
+        const int64_t per_block = kUThreads / c.G;
+        if (view->n_total > kShortMax) {
+            const int64_t max_medium = view->n_total / (kShortMax + 1) + 1;
+            const int gridM = (int)std::min<int64_t>((max_medium + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
+            launch_update(kKernelMedium, c, gridM, stream, P);
+            ETB_LAUNCHED();
+        }
         if (P.split_long && view->n_total > kLongThreshold) {
             const int64_t max_chunks = view->n_total / kLongChunk + 1;
-            const int64_t per_block = kUThreads / c.G;
             const int gridA = (int)std::min<int64_t>((max_chunks + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
             launch_update(kKernelPartials, c, gridA, stream, P);
             ETB_LAUNCHED();

@@ -170,8 +170,14 @@ class ShardedEnsemble:
                                  for q in range(p.world)]
         self._flag = torch.zeros(1, device="cuda")
         # owner q's cotangent buffer is rows[q] x B_global; my columns start at clo[rank]
+        # Destinations are visited in rotated order (rank+1, rank+2, ..., rank): if every rank started
+        # with peer 0 all of them would store into the same GPU at the same time (measured on 8 GPUs:
+        # 0.79 ms for the scatter vs 0.25 ms at link rate).
+        self._order = [(p.rank + 1 + k) % p.world for k in range(p.world)]
         self._scatter_ptrs = (C.c_void_p * p.world)(*[self._peer_dglob[q] + p.clo[p.rank] * p.rows[q] * es
-                                                      for q in range(p.world)])
+                                                      for q in self._order])
+        self._scatter_rows = (C.c_int64 * p.world)(*[p.rows[q] for q in self._order])
+        self._scatter_row_off = (C.c_int64 * p.world)(*[p.row_off[q] for q in self._order])
         dist.barrier(group=self.group)
 
     def _barrier(self):
@@ -194,7 +200,7 @@ class ShardedEnsemble:
         items, off = [], 0
         for t, i in zip(self.tables, Is):
             f = featuresize(t)
-            for q in range(p.world):                      # my rows of peer q's feature matrix, q's columns
+            for q in self._order:                         # my rows of peer q's feature matrix, q's columns
                 if p.cols[q]:
                     dst = self._peer_out_arrays[q].rows(p.row_off[p.rank] + off, p.row_off[p.rank] + off + f)
                     items.append(_item(t, i.cols(p.clo[q], p.chi[q]), dst))
@@ -207,8 +213,9 @@ class ShardedEnsemble:
 
     def _backward_fused(self, delta: DeviceArray):
         p = self.plan
-        _lib.check(_lib.lib().etb_a2a_scatter(self._scatter_ptrs, delta.ptr, delta.ld, self._rows, self._row_off, p.world,
-                                              p.my_cols, delta.elt, C.c_void_p(current_stream_ptr())))
+        _lib.check(_lib.lib().etb_a2a_scatter(self._scatter_ptrs, delta.ptr, delta.ld, self._scatter_rows,
+                                              self._scatter_row_off, p.world, p.my_cols, delta.elt,
+                                              C.c_void_p(current_stream_ptr())))
         self._barrier()
 
     def forward(self, I, out: DeviceArray = None) -> DeviceArray:

@@ -1,0 +1,183 @@
+#!/usr/bin/env python
+"""The other BASELINE.json configs (C1, C3, C5 sweep) on one B200.  Writes one JSON line per case to
+stdout (and to --out).  bench.py stays the contract benchmark (C2); this script is the measurement of
+SURVEY.md section 8d's remaining rows.
+
+  python tools/bench_configs.py --config c1|c3|c5 [--out file.jsonl]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "embeddingtables.jl_b200")):
+    sys.path.insert(0, p)
+import torch
+
+import bench
+import embtab as E
+
+PEAK, _ = bench.measured_peak_gbs()
+
+
+def timeit(fn, iters=20, warmup=5, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1.0)                      # write a buffer larger than L2 between iterations
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    return float(np.median(times))
+
+
+def rand_tables(nt, dim, nrows, static=True):
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    out = []
+    for _ in range(nt):
+        buf = torch.rand(dim * nrows, device="cuda", dtype=torch.float32, generator=gen)
+        out.append(E.SimpleEmbedding(E.DeviceArray(buf, (dim, nrows)), E.Static(dim) if static else None))
+    return out
+
+
+def emit(rec, fh):
+    line = json.dumps(rec)
+    print(line, flush=True)
+    if fh:
+        fh.write(line + "\n")
+        fh.flush()
+
+
+def zipf_indices(rng, nrows, n, alpha=1.05):
+    w = 1.0 / np.arange(1, nrows + 1, dtype=np.float64) ** alpha
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    ranks = np.searchsorted(cdf, rng.random(n))
+    perm = rng.permutation(nrows)
+    return (perm[ranks] + 1).astype(np.int64)
+
+
+def config_c1(fh):
+    """C1: 26 x (64 x 100k) f32, batch 2048, non-reducing maplookup + Descent update!.  27.7 MB forward /
+    41 MB update of algorithmic traffic: launch-latency bound, so the step is also timed as one CUDA graph."""
+    nt, dim, nrows, batch = 26, 64, 100_000, 2048
+    rng = np.random.default_rng(0xE7AB1E + 1)
+    tables = rand_tables(nt, dim, nrows)
+    I = E.DeviceArray.from_numpy(rng.integers(1, nrows + 1, (batch, nt)))
+    Is = list(E.colwrap(I))
+    outs = [E.DeviceArray.empty((dim, batch)) for _ in range(nt)]
+    deltas = [E.DeviceArray.from_numpy(rng.standard_normal((dim, batch)).astype(np.float32)) for _ in range(nt)]
+    grads = [E.SparseEmbeddingUpdate(E.Static(dim), d, i) for d, i in zip(deltas, Is)]
+    indexer, opt = E.Indexer(), E.Descent(0.01)
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda")   # 256 MB > L2
+
+    def fwd():
+        E.maplookup_(E.DefaultStrategy(), outs, tables, I)
+
+    def upd():
+        E.update_(opt, tables, grads, [indexer])
+
+    def step():
+        fwd(); upd()
+
+    t_fwd, t_upd, t_step = timeit(fwd, flush=flush), timeit(upd, flush=flush), timeit(step, flush=flush)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        step(); torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            step()
+    t_graph = timeit(g.replay, flush=flush)
+    u = sum(int(np.unique(i.numpy()).size) for i in Is)
+    fwd_bytes = nt * batch * (8 + 2 * dim * 4)
+    upd_bytes = nt * (batch * 8 + batch * dim * 4) + 2 * u * dim * 4
+    emit({"config": "C1", "shape": f"{nt} x ({dim} x {nrows}) f32, batch {batch}, gather + update!",
+          "fwd_us": t_fwd * 1e3, "update_us": t_upd * 1e3, "step_us": t_step * 1e3, "step_cuda_graph_us": t_graph * 1e3,
+          "lookups_per_step": nt * batch, "lookups_per_sec_graph": nt * batch / (t_graph * 1e-3),
+          "fwd_gbs": fwd_bytes / t_fwd / 1e6, "update_gbs": upd_bytes / t_upd / 1e6,
+          "roofline_time_us_at_measured_peak": (fwd_bytes + upd_bytes) / PEAK / 1e3,
+          "note": "L2 flushed between iterations; launch-bound (1 + 9 + 3 launches per step)"}, fh)
+
+
+def config_c3(fh):
+    """C3: one 128 x 10M f32 table, Zipf(1.05) indices: SparseEmbeddingUpdate + update!(Descent)."""
+    dim, nrows = 128, 10_000_000
+    rng = np.random.default_rng(0xE7AB1E + 3)
+    table = rand_tables(1, dim, nrows)[0]
+    indexer, opt = E.Indexer(), E.Descent(0.01)
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda")
+    cases = [("vector", 65536, 0), ("vector", 524288, 0), ("vector", 4194304, 0), ("pooled 32x16384", 524288, 32)]
+    for name, n, bag in cases:
+        idx = zipf_indices(rng, nrows, n)
+        batch = n if bag == 0 else n // bag
+        Ih = idx if bag == 0 else idx.reshape((bag, batch), order="F")
+        I = E.DeviceArray.from_numpy(Ih)
+        delta = E.DeviceArray(torch.randn(dim * batch, device="cuda"), (dim, batch))
+        grad = E.SparseEmbeddingUpdate(E.Static(dim), delta, I)
+        u = int(np.unique(idx).size)
+        top = int(np.bincount(idx).max())
+        bytes_alg = n * 8 + batch * dim * 4 + 2 * u * dim * 4
+        for mode in ("split", "strict"):
+            E.set_update_order(mode)
+            t = timeit(lambda: E.update_(opt, table, grad, indexer), iters=10 if mode == "split" else 3,
+                       warmup=2, flush=flush)
+            ti = timeit(lambda: E.index_(indexer, table, grad), iters=10, warmup=2, flush=flush)
+            emit({"config": "C3", "form": name, "n": n, "distinct_rows": u, "hottest_row_members": top, "order": mode,
+                  "update_us": t * 1e3, "index_us": ti * 1e3, "kernel_us": (t - ti) * 1e3,
+                  "lookups_per_sec": n / (t * 1e-3), "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / t / 1e6,
+                  "frac_of_measured_peak": bytes_alg / t / 1e6 / PEAK}, fh)
+        E.set_update_order("split")
+
+
+def config_c5(fh, quick=False):
+    """C5: pooled-lookup sweep, 26 tables x 1M rows, dim 16..256 x bag 1..128 x batch 1k..64k."""
+    nrows, nt = 1_000_000, 26
+    rng = np.random.default_rng(0xE7AB1E + 5)
+    dims = [16, 32, 64, 128, 256]
+    bags = [1, 2, 4, 8, 16, 32, 64, 128] if not quick else [1, 8, 32, 128]
+    batches = [1024, 4096, 16384, 65536] if not quick else [4096, 16384]
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda")
+    for dim in dims:
+        tables = rand_tables(nt, dim, nrows)
+        for batch in batches:
+            out = E.DeviceArray.empty((nt * dim, batch))
+            for bag in bags:
+                if nt * bag * batch * 8 > 12e9:
+                    continue
+                for dist in ("uniform", "zipf"):
+                    if dist == "uniform":
+                        I = E.DeviceArray(torch.randint(1, nrows + 1, (bag * batch * nt,), device="cuda", dtype=torch.int64),
+                                          (bag, batch, nt))
+                    else:
+                        if batch * bag > 2 ** 21:
+                            continue
+                        I = E.DeviceArray.from_numpy(np.stack(
+                            [zipf_indices(rng, nrows, bag * batch).reshape((bag, batch), order="F") for _ in range(nt)], axis=2))
+                    fn = lambda: E.maplookup_(E.PreallocationStrategy(0), out, tables, I)
+                    t = timeit(fn, iters=10, warmup=3, flush=flush if dist == "uniform" else None)
+                    b = nt * batch * (bag * (8 + dim * 4) + dim * 4)
+                    emit({"config": "C5", "dim": dim, "bag": bag, "batch": batch, "dist": dist, "us": t * 1e3,
+                          "lookups_per_sec": nt * batch * bag / (t * 1e-3), "gbs": b / t / 1e6,
+                          "frac_of_measured_peak": b / t / 1e6 / PEAK}, fh)
+                    del I
+        del tables
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c5", "c5quick"])
+    ap.add_argument("--out")
+    a = ap.parse_args()
+    E._lib.check(E.lib().etb_init(0))
+    fh = open(a.out, "a") if a.out else None
+    {"c1": config_c1, "c3": config_c3, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)
