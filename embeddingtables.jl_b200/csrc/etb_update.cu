@@ -37,6 +37,21 @@ constexpr int kUThreads = 256;
 #ifndef ETB_UPDATE_U
 #define ETB_UPDATE_U 1
 #endif
+#ifndef ETB_UPDATE_PREFETCH
+#define ETB_UPDATE_PREFETCH 1
+#endif
+#ifndef ETB_UPDATE_EXACT_MIN_BLOCKS
+#define ETB_UPDATE_EXACT_MIN_BLOCKS 4
+#endif
+#ifndef ETB_UPDATE_EXACT_UB
+#define ETB_UPDATE_EXACT_UB 4
+#endif
+#ifndef ETB_UPDATE_USE_EXACT
+#define ETB_UPDATE_USE_EXACT 1
+#endif
+#ifndef ETB_UPDATE_RPL
+#define ETB_UPDATE_RPL 1
+#endif
 #ifndef ETB_UPDATE_MIN_BLOCKS
 #define ETB_UPDATE_MIN_BLOCKS 2
 #endif
@@ -312,14 +327,16 @@ __global__ void __launch_bounds__(kUThreads, ETB_UPDATE_MIN_BLOCKS)
 sgd_update_kernel(const __grid_constant__ UpdParams P) {
     constexpr int UB = (ETB_UPDATE_UB / VPL) > 1 ? (ETB_UPDATE_UB / VPL) : 1;  // buckets in flight per group
     constexpr int U = (ETB_UPDATE_U / VPL) > 1 ? (ETB_UPDATE_U / VPL) : 1;  // extra member rows in flight
+    constexpr int RPL = ETB_UPDATE_RPL;                                       // records (buckets) per lane
+    constexpr int TILE = 32 * RPL;                                            // buckets per warp
     using V = Vec<T, VB>;
-    __shared__ TileMeta s_meta[kUThreads];
-    __shared__ TileMeta2 s_meta2[kUThreads];
+    __shared__ TileMeta s_meta[kUThreads * RPL];
+    __shared__ TileMeta2 s_meta2[kUThreads * RPL];
     const int G = P.G, nvec = P.nvec;
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
-    const int wbase = threadIdx.x & ~31;            // this warp's slice of the shared arrays
-    const int gbase = wbase + (lane & ~(G - 1));    // this group's slice
+    const int wbase = (threadIdx.x & ~31) * RPL;    // this warp's slice of the shared arrays
+    const int goff = lane & ~(G - 1);               // this group's first lane
     const unsigned gmask = group_mask(G, lane);
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
@@ -333,12 +350,15 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         s_end = min((int64_t)P.this_split * split, nnz);
     }
     const int64_t warp_id = (int64_t)blockIdx.x * (kUThreads / 32) + threadIdx.x / 32;
-    const int64_t t0 = s_begin + warp_id * 32;
+    const int64_t t0 = s_begin + warp_id * TILE;
     if (t0 >= s_end) return;
 
-    {   // ---- tile metadata: lane l describes bucket t0 + l
-        const bool valid = t0 + lane < s_end;
-        const int64_t s = valid ? t0 + lane : s_end - 1;
+    // ---- tile metadata: lane l describes buckets t0 + l (+ 32, ...)
+#pragma unroll
+    for (int r = 0; r < RPL; ++r) {
+        const int64_t sb = t0 + r * 32 + lane;
+        const bool valid = sb < s_end;
+        const int64_t s = valid ? sb : s_end - 1;
         const uint4 raw = __ldg((const uint4*)(P.recs + s));
         const int64_t start = raw.x;
         const int64_t stop = (s + 1 < nnz) ? (int64_t)__ldg(&P.recs[s + 1].start) : P.n_total;
@@ -355,8 +375,14 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         TileMeta m;
         m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
         m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
-        s_meta[threadIdx.x] = m;
-        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, 0};
+        if (ETB_UPDATE_PREFETCH && VB == 16 && cnt > 0) {
+            // the whole tile's rows start streaming DRAM -> L2 now; the register loads below then
+            // find them in L2 (in-flight bytes no longer limited by registers)
+            prefetch_row_l2(m.row, (uint32_t)nvec * VB);
+            prefetch_row_l2(m.d0, (uint32_t)nvec * VB);
+        }
+        s_meta[wbase + r * 32 + lane] = m;
+        s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0, 0};
     }
     __syncwarp();
 
@@ -364,46 +390,147 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         int vi[VPL];
 #pragma unroll
         for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
-
-        for (int k0 = 0; k0 < G; k0 += UB) {
-            // the old table row and the first delta row of UB buckets, all in flight together
-            V old[UB][VPL], v0[UB][VPL];
+        for (int r = 0; r < RPL; ++r) {
+            const int gbase = wbase + r * 32 + goff;  // my group's buckets of this 32-record slab
+            for (int k0 = 0; k0 < G; k0 += UB) {
+                // the old table row and the first delta row of UB buckets, all in flight together
+                V old[UB][VPL], v0[UB][VPL];
 #pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                if (k0 + u < G && s_meta2[gbase + k0 + u].cnt > 0) {
-                    const TileMeta m = s_meta[gbase + k0 + u];
-#pragma unroll
-                    for (int p = 0; p < VPL; ++p) {
-                        ld_plain<VB>(&old[u][p], m.row + vi[p]);
-                        ld_row<VB>(&v0[u][p], m.d0 + vi[p]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                if (k0 + u < G) {
-                    const TileMeta2 m2 = s_meta2[gbase + k0 + u];
-                    if (m2.cnt > 0) {
-                        V acc[VPL];  // accum = zero(Tiled), then += members in order (src/sparseupdate.jl:114-120)
-#pragma unroll
-                        for (int p = 0; p < VPL; ++p)
-#pragma unroll
-                            for (int e = 0; e < V::NE; ++e) acc[p].e[e] = T(0) + v0[u][p].e[e];
-                        if (m2.cnt > 1)  // a few duplicates (<= kShortMax members): the rest, strictly in order
-                            accumulate_members<T, VB, VPL, U>(acc, P.item[m2.slot], P.map, (int64_t)m2.start + 1,
-                                                              (int64_t)m2.start + m2.cnt, vi, G, gl, lane, gmask);
-                        char* row = const_cast<char*>(s_meta[gbase + k0 + u].row);
+                for (int u = 0; u < UB; ++u) {
+                    if (k0 + u < G && s_meta2[gbase + k0 + u].cnt > 0) {
+                        const TileMeta m = s_meta[gbase + k0 + u];
 #pragma unroll
                         for (int p = 0; p < VPL; ++p) {
-                            if (pass0 + gl + p * G < nvec) {
-                                V out;
+                            ld_plain<VB>(&old[u][p], m.row + vi[p]);
+                            ld_row<VB>(&v0[u][p], m.d0 + vi[p]);
+                        }
+                    }
+                }
 #pragma unroll
-                                for (int e = 0; e < V::NE; ++e)
-                                    out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[p].e[e], eta, fma);
-                                st_plain<VB>(row + vi[p], &out);
+                for (int u = 0; u < UB; ++u) {
+                    if (k0 + u < G) {
+                        const TileMeta2 m2 = s_meta2[gbase + k0 + u];
+                        if (m2.cnt > 0) {
+                            V acc[VPL];  // accum = zero(Tiled), then += members in order (src/sparseupdate.jl:114-120)
+#pragma unroll
+                            for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                                for (int e = 0; e < V::NE; ++e) acc[p].e[e] = T(0) + v0[u][p].e[e];
+                            if (m2.cnt > 1)  // a few duplicates (<= kShortMax members): the rest, strictly in order
+                                accumulate_members<T, VB, VPL, U>(acc, P.item[m2.slot], P.map, (int64_t)m2.start + 1,
+                                                                  (int64_t)m2.start + m2.cnt, vi, G, gl, lane, gmask);
+                            char* row = const_cast<char*>(s_meta[gbase + k0 + u].row);
+#pragma unroll
+                            for (int p = 0; p < VPL; ++p) {
+                                if (pass0 + gl + p * G < nvec) {
+                                    V out;
+#pragma unroll
+                                    for (int e = 0; e < V::NE; ++e)
+                                        out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[p].e[e], eta, fma);
+                                    st_plain<VB>(row + vi[p], &out);
+                                }
                             }
                         }
                     }
+                }
+            }
+        }
+    }
+}
+
+// Exact-fit specialisation of the main kernel: VB = 16 and the row is exactly G*VPL vectors (every
+// power-of-two dim, e.g. dim 128 f32 -> G = 32, VPL = 1).  G, the vector offsets and the single pass
+// are compile-time, the few-duplicates loop needs no shuffles (every lane reads the same map entry:
+// one broadcast transaction), so the kernel fits in few registers and runs at 3-4x the occupancy of
+// the generic one -- which is what the random 512-byte read-modify-write pattern wants: the HBM
+// ceiling (6.5 TB/s, tools/ubench_rmw.cu) is reached with only 4 rows in flight per warp but needs
+// ~all warp slots filled.
+template <typename T, int VPL, int G, int UB>
+__global__ void __launch_bounds__(kUThreads, ETB_UPDATE_EXACT_MIN_BLOCKS)
+sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int VB = 16;
+    using V = Vec<T, VB>;
+    __shared__ TileMeta s_meta[kUThreads];
+    __shared__ TileMeta2 s_meta2[kUThreads];
+    const int lane = threadIdx.x & 31;
+    const int voff = (lane & (G - 1)) * VB;                  // my first vector of a row
+    const int gbase = threadIdx.x & ~(G - 1);                // my group's slice of the shared arrays
+    const int64_t nnz = *P.nnz;
+    int64_t s_begin = 0, s_end = nnz;
+    if (P.num_splits > 0) {
+        const int64_t split = nnz / P.num_splits + 1;
+        s_begin = (int64_t)(P.this_split - 1) * split;
+        s_end = min((int64_t)P.this_split * split, nnz);
+    }
+    const int64_t t0 = s_begin + (((int64_t)blockIdx.x * kUThreads + threadIdx.x) >> 5) * 32;
+    if (t0 >= s_end) return;
+    {   // ---- tile metadata: lane l describes bucket t0 + l
+        const bool valid = t0 + lane < s_end;
+        const int64_t s = valid ? t0 + lane : s_end - 1;
+        const uint4 raw = __ldg((const uint4*)(P.recs + s));
+        const int64_t stop = (s + 1 < nnz) ? (int64_t)__ldg(&P.recs[s + 1].start) : P.n_total;
+        const uint64_t key = ((uint64_t)raw.w << 32) | raw.z;
+        const int slot = (int)(key >> P.row_bits) - P.slot0;
+        const bool mine = valid && slot >= 0 && slot < P.nslots;
+        const UpdDesc& md = P.item[mine ? slot : 0];
+        int cnt = mine ? (int)(stop - (int64_t)raw.x) : 0;
+        if (cnt > kShortMax) {
+            if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            else P.mediums[atomicAdd(&P.counters->n_medium, 1u)] = (uint32_t)s;
+            cnt = 0;
+        }
+        const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+        TileMeta m;
+        m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
+        m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
+        s_meta[threadIdx.x] = m;
+        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, 0};
+    }
+    __syncwarp();
+    const T eta = (T)P.eta;
+    const bool fma = P.fma != 0;
+#pragma unroll 1
+    for (int k0 = 0; k0 < G; k0 += UB) {
+        V old[UB][VPL], acc[UB][VPL];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            if (s_meta2[gbase + k0 + u].cnt > 0) {
+                const TileMeta m = s_meta[gbase + k0 + u];
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) {
+                    ld_plain<VB>(&old[u][p], m.row + voff + p * G * VB);
+                    ld_row<VB>(&acc[u][p], m.d0 + voff + p * G * VB);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const TileMeta2 m2 = s_meta2[gbase + k0 + u];
+            if (m2.cnt > 0) {
+#pragma unroll
+                for (int p = 0; p < VPL; ++p)
+#pragma unroll
+                    for (int e = 0; e < V::NE; ++e) acc[u][p].e[e] = T(0) + acc[u][p].e[e];  // accum = zero + first
+                if (m2.cnt > 1) {  // up to kShortMax-1 more members, strictly in order
+                    const UpdDesc& d = P.item[m2.slot];
+                    for (int i = 1; i < m2.cnt; ++i) {
+                        const char* r = d.delta + (int64_t)__ldg(P.map + m2.start + i) * d.ld_delta_bytes + voff;
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) {
+                            V v;
+                            ld_row<VB>(&v, r + p * G * VB);
+#pragma unroll
+                            for (int e = 0; e < V::NE; ++e) acc[u][p].e[e] = acc[u][p].e[e] + v.e[e];
+                        }
+                    }
+                }
+                char* row = const_cast<char*>(s_meta[gbase + k0 + u].row) + voff;
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) {
+                    V out;
+#pragma unroll
+                    for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[u][p].e[e], eta, fma);
+                    st_plain<VB>(row + p * G * VB, &out);
                 }
             }
         }
@@ -617,7 +744,25 @@ static void launch_update_vb(int which, const UpdClass& c, int grid, cudaStream_
     return launch_update_vpl<T, 16>(which, c.vpl, grid, s, P);
 }
 
+template <typename T>
+static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+    constexpr int UB = ETB_UPDATE_EXACT_UB;
+    if (c.vb != 16 || c.nvec != c.G * c.vpl) return false;
+#define ETB_EXACT(VPLV, GV, UBV)                                                         \
+    if (c.vpl == VPLV && c.G == GV) {                                                    \
+        sgd_update_exact_kernel<T, VPLV, GV, (UBV)><<<grid, kUThreads, 0, s>>>(P);       \
+        return true;                                                                     \
+    }
+    ETB_EXACT(1, 32, UB) ETB_EXACT(1, 16, UB) ETB_EXACT(1, 8, UB) ETB_EXACT(1, 4, UB < 4 ? UB : 4)
+    ETB_EXACT(2, 32, UB > 2 ? UB / 2 : 1) ETB_EXACT(4, 32, 1)
+#undef ETB_EXACT
+    return false;
+}
+
 static void launch_update(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+    if (which == kKernelMain && ETB_UPDATE_USE_EXACT) {
+        if (c.elt == ETB_F32 ? launch_update_exact<float>(c, grid, s, P) : launch_update_exact<double>(c, grid, s, P)) return;
+    }
     if (c.elt == ETB_F32) launch_update_vb<float>(which, c, grid, s, P);
     else launch_update_vb<double>(which, c, grid, s, P);
 }
@@ -769,7 +914,7 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         P.G = c.G;
         P.nvec = c.nvec;
         ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
-        const int64_t buckets_per_block = (kUThreads / 32) * 32;  // one 32-bucket tile per warp
+        const int64_t buckets_per_block = (kUThreads / 32) * 32 * ETB_UPDATE_RPL;  // one tile per warp
         const int grid = (int)((view->n_total + buckets_per_block - 1) / buckets_per_block);
         launch_update(kKernelMain, c, grid, stream, P);
         ETB_LAUNCHED();

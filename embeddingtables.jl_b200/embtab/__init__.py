@@ -9,7 +9,7 @@ from .darray import DeviceArray, as_device, as_device_indices, pinned_empty
 from .lookup import (AbstractExecutionStrategy, ColumnWrap, DefaultStrategy, PreallocationStrategy,
                      SimpleParallelStrategy, colwrap, destination, lookup, lookup_, maplookup, maplookup_)
 from .sparseupdate import (AbstractIndexer, DenseIndexer, Descent, Indexer, IndexerView, Slicer,
-                           SparseEmbeddingUpdate, SparseIndexer, ensemble_update, index_, pullback, rrule,
+                           SparseEmbeddingUpdate, SparseIndexer, ensemble_update, index_, prefetch_index, pullback, rrule,
                            set_update_order,
                            uncompress, update_, update_table_)
 from .tables import (AbstractEmbeddingTable, ArgumentError, Dynamic, Forward, IndexingContext, NoContext,

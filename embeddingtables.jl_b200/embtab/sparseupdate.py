@@ -78,6 +78,8 @@ class Indexer(AbstractIndexer):
         self.workspace = None
         self.view = None     # _lib.IndexView of the last index!
         self._items = None
+        self._event = None   # set by prefetch_index: the side stream's completion event
+        self._prefetched = None
 
     def _ensure(self, items_arr, n):
         need = C.c_size_t()
@@ -125,11 +127,52 @@ def _peek(ptr, n, dtype):
     return out
 
 
+class _IndicesOnly:
+    """what index! needs of a SparseEmbeddingUpdate when the cotangent does not exist yet"""
+
+    def __init__(self, table, indices):
+        self.indices = as_device_indices(indices)
+
+
+def _index_item(table, g) -> _lib.UpdateItem:
+    if isinstance(g, _IndicesOnly):
+        I = g.indices
+        bag, batch, ld_idx = (0, I.shape[0], 0) if I.ndim == 1 else (I.shape[0], I.shape[1], I.ld)
+        return _lib.UpdateItem(table.descriptor(), None, featuresize(table), I.ptr, batch, bag, ld_idx, I.elt, 0)
+    return _update_item(table, g)
+
+
+_SIDE_STREAM = {}
+
+
+def prefetch_index(indexer: Indexer, tables, indices):
+    """GPU-only extension: start index! for (tables, indices) NOW, on a side stream.
+
+    index! depends only on the indices, not on the cotangent, so it can overlap the forward pass (and,
+    for host-resident data, the PCIe copies).  A following update!(opt, tables, grads, [indexer]) on the
+    same tables and indices waits for the side stream and skips its own index! phase."""
+    single = isinstance(tables, AbstractEmbeddingTable)
+    tables = [tables] if single else list(tables)
+    Is = [indices] if single else list(colwrap(indices))
+    dev = torch.cuda.current_device()
+    side = _SIDE_STREAM.get(dev)
+    if side is None:
+        side = _SIDE_STREAM[dev] = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        index_(indexer, tables, [_IndicesOnly(t, i) for t, i in zip(tables, Is)])
+        indexer._event = side.record_event()
+    indexer._prefetched = [i.ptr for i in (g.indices for g in indexer._grads_keepalive)]
+    return indexer
+
+
 def index_(indexer: Indexer, tables, grads):
     """index!(indexer, indices, maxindex) for one table or an ensemble sharing one Indexer."""
     if isinstance(tables, AbstractEmbeddingTable):
         tables, grads = [tables], [grads]
-    items = [_update_item(t, g) for t, g in zip(tables, grads)]
+    items = [_index_item(t, g) for t, g in zip(tables, grads)]
+    indexer._grads_keepalive = list(grads)
+    indexer._event, indexer._prefetched = None, None
     arr = (_lib.UpdateItem * len(items))(*items)
     indexer._ensure(arr, len(items))
     view = _lib.IndexView()
@@ -199,17 +242,31 @@ def update_(opt: Descent, table, grad, indexer=None, nontemporal=True, *args, nu
     if isinstance(table, AbstractEmbeddingTable):
         if indexer is None:
             indexer = Indexer()
-        index_(indexer, table, grad)
+        if not _consume_prefetch(indexer, [table], [grad]):
+            index_(indexer, table, grad)
         _apply([table], [grad], indexer, opt.eta)  # convert(eltype(table), opt.eta) happens in the kernel
         return None
     tables, grads = list(table), list(grad)
     indexers = indexer if indexer is not None else [Indexer()]
     ix = indexers[0] if isinstance(indexers, (list, tuple)) else indexers
-    index_(ix, tables, grads)  # one batched sort for every table (the @batch index! phase, :211-213)
+    if not _consume_prefetch(ix, tables, grads):
+        index_(ix, tables, grads)  # one batched sort for every table (the @batch index! phase, :211-213)
     if telemetry_cb is not None:
         telemetry_cb()
     _apply(tables, grads, ix, opt.eta)
     return None
+
+
+def _consume_prefetch(indexer: Indexer, tables, grads) -> bool:
+    """True if `indexer` holds a prefetch_index result for exactly these index arrays: wait for it and
+    rebuild the item descriptors with the real cotangents."""
+    if indexer._prefetched is None or indexer._prefetched != [g.indices.ptr for g in grads]:
+        return False
+    torch.cuda.current_stream().wait_event(indexer._event)
+    items = [_update_item(t, g) for t, g in zip(tables, grads)]
+    indexer._items = (_lib.UpdateItem * len(items))(*items)
+    indexer._event, indexer._prefetched = None, None
+    return True
 
 
 def ensemble_update(nthreads: int):

@@ -273,3 +273,32 @@ def test_split_long_zipf(E, O, dim, dtype, order):
             assert short.sum() > 0 and (~short).sum() > 0
             assert np.array_equal(got[:, short], ref.data[:, short])
             assert np.linalg.norm(got - ref.data) <= RTOL * np.linalg.norm(ref.data)
+
+
+def test_prefetch_index_overlapped(E, O):
+    # index! started early on a side stream (GPU-only extension) gives the same update, single and ensemble
+    rng = np.random.default_rng(21)
+    base = [rng.standard_normal((64, 400)).astype(np.float32) for _ in range(3)]
+    I = rng.integers(1, 401, (6, 300, 3))
+    deltas = [rng.standard_normal((64, 300)).astype(np.float32) for _ in range(3)]
+    tables = [E.SimpleEmbedding(b.copy(), E.Static(64)) for b in base]
+    ix = E.Indexer()
+    Id = E.as_device_indices(I)
+    E.prefetch_index(ix, tables, Id)
+    out = E.maplookup(E.PreallocationStrategy(), tables, Id)          # overlaps the side stream
+    grads = [E.SparseEmbeddingUpdate(E.Static(64), d, i) for d, i in zip(deltas, E.colwrap(Id))]
+    assert ix._prefetched is not None
+    E.update_(E.Descent(0.3), tables, grads, [ix])
+    assert ix._prefetched is None                                      # consumed
+    for t, b, d, k in zip(tables, base, deltas, range(3)):
+        ref = O.Table(b.copy(order="F"), static=True)
+        O.update(ref, d, I[:, :, k], 0.3)
+        assert np.array_equal(t.to_numpy(), ref.data)
+    # a prefetch for OTHER indices is ignored (falls back to a fresh index!)
+    t1 = E.SimpleEmbedding(base[0].copy(), E.Static(64))
+    E.prefetch_index(ix, t1, E.as_device_indices(I[:, :, 1]))
+    g = E.SparseEmbeddingUpdate(E.Static(64), deltas[0], I[:, :, 0])
+    E.update_(E.Descent(0.3), t1, g, ix)
+    ref = O.Table(base[0].copy(order="F"), static=True)
+    O.update(ref, deltas[0], I[:, :, 0], 0.3)
+    assert np.array_equal(t1.to_numpy(), ref.data)
