@@ -235,15 +235,43 @@ def run_ours(args):
         launches["update"] = lib.etb_last_launch_count()
         if events: events[3].record()
 
+    # e2e: every step copies ITS indices and cotangent in from pinned host memory and its feature
+    # matrix out.  The only cross-step pipelining is the standard input double buffer: step k+1's
+    # indices are uploaded on a copy stream while step k's result is downloaded (H2D and D2H use
+    # different copy engines).  Within a step the dependency chain is kept: forward -> result on the
+    # host -> cotangent from the host -> update.
+    copy_stream = torch.cuda.Stream()
+    I_buf = [I_dev, E.DeviceArray.empty((BAG, BATCH, NT), np.int64)]
+    Is_buf = [Is, list(E.colwrap(I_buf[1]))]
+    idx_ready = [None, None]
+    buf_free = [None, None]
+    e2e_state = {"k": 0}
+
+    def upload_indices(slot):
+        with torch.cuda.stream(copy_stream):
+            if buf_free[slot] is not None:
+                copy_stream.wait_event(buf_free[slot])    # the step that last used this buffer is done
+            I_buf[slot].upload(idx_pinned)                # H2D: that step's indices
+            idx_ready[slot] = copy_stream.record_event()
+
     def step_e2e():
-        I_dev.upload(idx_pinned)                          # H2D: this step's indices
-        E.prefetch_index(indexer, tables, Is)             # side stream: overlaps forward + PCIe copies
-        E.maplookup_(strategy, out_dev, tables, I_dev)
+        k = e2e_state["k"]
+        slot = k % 2
+        if idx_ready[slot] is None:
+            upload_indices(slot)
+        main = torch.cuda.current_stream()
+        main.wait_event(idx_ready[slot])
+        idx_ready[slot] = None
+        E.prefetch_index(indexer, tables, Is_buf[slot])   # side stream: overlaps forward + PCIe copies
+        E.maplookup_(strategy, out_dev, tables, I_buf[slot])
+        upload_indices(1 - slot)                          # next step's indices, behind this step's D2H
         out_dev.download(out_pinned)                      # D2H: the step's result (feature matrix)
         delta_dev.upload(delta_pinned)                    # H2D: the upstream cotangent
         slicer = E.Slicer(PREPEND + 1, 1, delta_dev)
-        grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is]
+        grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is_buf[slot]]
         E.update_(opt, tables, grads, [indexer])
+        buf_free[slot] = main.record_event()
+        e2e_state["k"] = k + 1
 
     def sync():
         torch.cuda.synchronize()

@@ -10,7 +10,8 @@
 // actually use (cub::DeviceRadixSort -- library code, like cuBLAS would be for a GEMM), so
 // members of a bucket stay in occurrence order = the order remap! records (src/utils.jl:
 // 481-511).  Bucket starts are the positions whose key differs from the previous one,
-// compacted by cub::DeviceSelect.  Buckets come out in ascending (table, row) order instead
+// compacted into one 16-byte record per bucket by three small hand-written kernels (count heads per
+// tile, scan the tile counts, write records).  Buckets come out in ascending (table, row) order instead
 // of the reference's first-seen order; buckets are disjoint table rows, so results do not
 // depend on that order.
 //
@@ -21,9 +22,6 @@
 // (:88).  One bucket = one row = one writer: no atomics anywhere.
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_select.cuh>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
 #include <vector>
 
 #include "etb_common.cuh"
@@ -82,7 +80,7 @@ struct IndexLayout {
     int64_t n_total;
     int32_t row_bits, slot_bits, key_bytes;
     size_t max_long, max_chunks, max_medium, partial_pitch;
-    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_counters, off_long, off_chunks, off_medium, off_partials,
+    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_tiles, off_counters, off_long, off_chunks, off_medium, off_partials,
         off_temp, temp_bytes, total;
 };
 
@@ -94,31 +92,140 @@ static int bits_for(uint64_t count) {  // bits needed to represent 0 .. count-1
 
 static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-template <typename KeyT>
-struct MakeRec {
-    const KeyT* keys;
-    const int32_t* map;
-    __device__ __forceinline__ BucketRec operator()(int32_t p) const {
-        BucketRec r;
-        r.start = (uint32_t)p;
-        r.m0 = map[p];
-        r.key = (uint64_t)keys[p];
-        return r;
-    }
-};
-template <typename KeyT>
-struct IsHead {
-    const KeyT* keys;
-    __device__ __forceinline__ bool operator()(const BucketRec& r) const {
-        return r.start == 0 || (uint64_t)keys[r.start - 1] != r.key;
-    }
-};
+// ---- bucket heads -> records (hand-written replacement of a library stream compaction) ----------
+// Position p is a bucket head when its key differs from the previous one.  Three small kernels:
+// count heads per 4096-position tile, scan the tile counts (one block), write one record per head
+// at its rank.  Positions are striped over the block (p = base + i*256 + tid) so every load is
+// coalesced; ranks follow position order (i-major, then warp, then lane) via warp ballots.
+constexpr int kSelThreads = 256, kSelItems = 16, kSelTile = kSelThreads * kSelItems;
 
 template <typename KeyT>
-static cudaError_t select_heads(void* temp, size_t& temp_bytes, const KeyT* keys, const int32_t* map, BucketRec* recs,
-                                int64_t* nnz, int64_t n, cudaStream_t stream) {
-    auto in = thrust::make_transform_iterator(thrust::counting_iterator<int32_t>(0), MakeRec<KeyT>{keys, map});
-    return cub::DeviceSelect::If(temp, temp_bytes, in, recs, nnz, (int32_t)n, IsHead<KeyT>{keys}, stream);
+__device__ __forceinline__ uint32_t head_flags(const KeyT* __restrict__ keys, int64_t base, int64_t n, KeyT (&k)[kSelItems]) {
+    uint32_t flags = 0;
+#pragma unroll
+    for (int i = 0; i < kSelItems; ++i) {
+        const int64_t p = base + i * kSelThreads + threadIdx.x;
+        if (p < n) {
+            k[i] = __ldg(keys + p);
+            if (p == 0 || __ldg(keys + p - 1) != k[i]) flags |= 1u << i;
+        }
+    }
+    return flags;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSelThreads) count_heads_kernel(const KeyT* __restrict__ keys, int64_t n,
+                                                                   uint32_t* __restrict__ tile_counts) {
+    __shared__ uint32_t warp_sums[kSelThreads / 32];
+    KeyT k[kSelItems];
+    uint32_t c = __popc(head_flags(keys, (int64_t)blockIdx.x * kSelTile, n, k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < kSelThreads / 32; ++w) t += warp_sums[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan of the tile counts in place (one block of 1024 threads), total -> nnz
+__global__ void __launch_bounds__(1024) scan_tile_counts_kernel(uint32_t* __restrict__ counts, int ntiles,
+                                                                int64_t* __restrict__ nnz) {
+    __shared__ uint32_t warp_tot[32];
+    const int per = (ntiles + 1023) / 1024;
+    const int lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += counts[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t w = warp_tot[threadIdx.x], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (threadIdx.x >= o) wi += v;
+        }
+        warp_tot[threadIdx.x] = wi - w;  // exclusive warp offsets
+        if (threadIdx.x == 31) *nnz = (int64_t)wi;
+    }
+    __syncthreads();
+    uint32_t run = warp_tot[threadIdx.x >> 5] + incl - sum;
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t c = counts[i];
+        counts[i] = run;
+        run += c;
+    }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSelThreads) write_records_kernel(const KeyT* __restrict__ keys,
+                                                                     const int32_t* __restrict__ map, int64_t n,
+                                                                     const uint32_t* __restrict__ tile_offsets,
+                                                                     BucketRec* __restrict__ recs) {
+    __shared__ uint32_t cnt[kSelItems][kSelThreads / 32];  // heads per (item row, warp), then exclusive offsets
+    const int64_t base = (int64_t)blockIdx.x * kSelTile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    KeyT k[kSelItems];
+    const uint32_t flags = head_flags(keys, base, n, k);
+    uint32_t before[kSelItems];  // heads of lower lanes in my warp, per item row
+#pragma unroll
+    for (int i = 0; i < kSelItems; ++i) {
+        const uint32_t ballot = __ballot_sync(0xffffffffu, (flags >> i) & 1u);
+        before[i] = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) cnt[i][warp] = __popc(ballot);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive scan of the 16 x 8 counts in position order (4 per lane)
+        constexpr int kCells = kSelItems * (kSelThreads / 32), kPer = kCells / 32;
+        uint32_t* flat = &cnt[0][0];
+        uint32_t v[kPer], sum = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { v[j] = flat[threadIdx.x * kPer + j]; sum += v[j]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) { flat[threadIdx.x * kPer + j] = run; run += v[j]; }
+    }
+    __syncthreads();
+    const uint32_t tile_off = tile_offsets[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < kSelItems; ++i) {
+        if ((flags >> i) & 1u) {
+            const int64_t p = base + i * kSelThreads + threadIdx.x;
+            BucketRec r;
+            r.start = (uint32_t)p;
+            r.m0 = __ldg(map + p);
+            r.key = (uint64_t)k[i];
+            recs[tile_off + cnt[i][warp] + before[i]] = r;
+        }
+    }
+}
+
+template <typename KeyT>
+static int32_t select_heads(uint32_t* tile_counts, const KeyT* keys, const int32_t* map, BucketRec* recs, int64_t* nnz,
+                            int64_t n, cudaStream_t stream) {
+    const int ntiles = (int)((n + kSelTile - 1) / kSelTile);
+    count_heads_kernel<KeyT><<<ntiles, kSelThreads, 0, stream>>>(keys, n, tile_counts);
+    ETB_LAUNCHED();
+    scan_tile_counts_kernel<<<1, 1024, 0, stream>>>(tile_counts, ntiles, nnz);
+    ETB_LAUNCHED();
+    write_records_kernel<KeyT><<<ntiles, kSelThreads, 0, stream>>>(keys, map, n, tile_counts, recs);
+    ETB_LAUNCHED();
+    return ETB_OK;
 }
 
 static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexLayout& L) {
@@ -153,27 +260,26 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     for (int b = 0; b < 2; ++b) { L.off_vals[b] = off; off = align_up(off + n * sizeof(int32_t)); }
     L.off_recs = off; off = align_up(off + (n + 1) * sizeof(BucketRec));
     L.off_nnz = off; off = align_up(off + sizeof(int64_t));
+    L.off_tiles = off; off = align_up(off + ((n + kSelTile - 1) / kSelTile + 1) * sizeof(uint32_t));
     L.off_counters = off; off = align_up(off + sizeof(LongCounters));
     L.off_long = off; off = align_up(off + L.max_long * sizeof(LongRec));
     L.off_chunks = off; off = align_up(off + L.max_chunks * sizeof(ChunkRec));
     L.off_medium = off; off = align_up(off + L.max_medium * sizeof(uint32_t));
     L.off_partials = off; off = align_up(off + L.max_chunks * L.partial_pitch);
-    // CUB temp storage: max over the sort and the select
-    size_t t_sort = 0, t_sel = 0;
+    // CUB temp storage of the radix sort
+    size_t t_sort = 0;
     const int end_bit = L.row_bits + L.slot_bits;
     if (L.key_bytes == 4) {
         cub::DoubleBuffer<uint32_t> k(nullptr, nullptr);
         cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
         ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
-        ETB_CUDA(select_heads<uint32_t>(nullptr, t_sel, nullptr, nullptr, nullptr, nullptr, (int64_t)n, 0));
     } else {
         cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
         cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
         ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
-        ETB_CUDA(select_heads<uint64_t>(nullptr, t_sel, nullptr, nullptr, nullptr, nullptr, (int64_t)n, 0));
     }
     L.off_temp = off;
-    L.temp_bytes = std::max(t_sort, t_sel);
+    L.temp_bytes = t_sort;
     L.total = align_up(off + L.temp_bytes);
     return ETB_OK;
 }
@@ -778,6 +884,7 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
     char* base = (char*)ws;
     BucketRec* recs = (BucketRec*)(base + L.off_recs);
     int64_t* nnz = (int64_t*)(base + L.off_nnz);
+    uint32_t* tiles = (uint32_t*)(base + L.off_tiles);
     int32_t* vals[2] = {(int32_t*)(base + L.off_vals[0]), (int32_t*)(base + L.off_vals[1])};
     void* keys[2] = {base + L.off_keys[0], base + L.off_keys[1]};
     const int end_bit = L.row_bits + L.slot_bits;
@@ -821,26 +928,63 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
             }
             ETB_LAUNCHED();
         }
-        // K4b: stable radix sort over the used key bits, then one record per bucket head
-        size_t temp_bytes = L.temp_bytes;
-        void* temp = base + L.off_temp;
-        cub::DoubleBuffer<int32_t> v(vals[0], vals[1]);
-        if (L.key_bytes == 4) {
-            cub::DoubleBuffer<uint32_t> k((uint32_t*)keys[0], (uint32_t*)keys[1]);
-            ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, L.n_total, 0, end_bit, stream));
-            keys[0] = k.Current();
-            temp_bytes = L.temp_bytes;
-            ETB_CUDA(select_heads<uint32_t>(temp, temp_bytes, (const uint32_t*)keys[0], v.Current(), recs, nnz, L.n_total, stream));
-        } else {
-            cub::DoubleBuffer<uint64_t> k((uint64_t*)keys[0], (uint64_t*)keys[1]);
-            ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, L.n_total, 0, end_bit, stream));
-            keys[0] = k.Current();
-            temp_bytes = L.temp_bytes;
-            ETB_CUDA(select_heads<uint64_t>(temp, temp_bytes, (const uint64_t*)keys[0], v.Current(), recs, nnz, L.n_total, stream));
+        // K4b: stable radix sort over the used key bits, then one record per bucket head.
+        // The pairs of one table are contiguous and tables are in slot order, so the ensemble can be
+        // sorted as 2^r groups of consecutive slots on the low (row_bits + slot_bits - r) bits only --
+        // the keys keep their full slot; inside a group the dropped top bits are constant.  When that
+        // saves a whole 8-bit radix pass over all the data (C2: 25 bits -> 24: 4 passes -> 3) it is
+        // worth the few extra launches.
+        int drop = 0;
+        if (L.n_total >= (1 << 20)) {
+            for (int r = 1; r <= std::min(L.slot_bits, 3); ++r)
+                if ((end_bit - r + 7) / 8 < (end_bit + 7) / 8) { drop = r; break; }
         }
-        vals[0] = v.Current();
-        // CUB launches: histogram + exclusive sum + one onesweep pass per 8 key bits; select = init + sweep
-        launch_counter() += 2 + (end_bit + 7) / 8 + 2;
+        const int sort_bits = end_bit - drop;
+        const int slots_per_group = 1 << (L.slot_bits - drop);
+        std::vector<int64_t> group_start;  // pair offset of each group (+ end)
+        {
+            int64_t off = 0;
+            for (int i = 0; i < n_items; ++i) {
+                if (i % slots_per_group == 0) group_start.push_back(off);
+                off += items[i].batch * (items[i].bag ? items[i].bag : 1);
+            }
+            group_start.push_back(off);
+        }
+        void* temp = base + L.off_temp;
+        void* keys_out = nullptr;
+        int32_t* vals_out = nullptr;
+        for (size_t g = 0; g + 1 < group_start.size(); ++g) {
+            const int64_t g0 = group_start[g], gn = group_start[g + 1] - g0;
+            if (gn == 0) continue;
+            size_t temp_bytes = L.temp_bytes;
+            cub::DoubleBuffer<int32_t> v(vals[0] + g0, vals[1] + g0);
+            void* kcur;
+            if (L.key_bytes == 4) {
+                cub::DoubleBuffer<uint32_t> k((uint32_t*)keys[0] + g0, (uint32_t*)keys[1] + g0);
+                ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, gn, 0, sort_bits, stream));
+                kcur = k.Current() - g0;
+            } else {
+                cub::DoubleBuffer<uint64_t> k((uint64_t*)keys[0] + g0, (uint64_t*)keys[1] + g0);
+                ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, gn, 0, sort_bits, stream));
+                kcur = k.Current() - g0;
+            }
+            int32_t* vcur = v.Current() - g0;
+            if (!keys_out) { keys_out = kcur; vals_out = vcur; }
+            if (kcur != keys_out) {  // a group that ended in the other ping-pong buffer (different pass parity)
+                ETB_CUDA(cudaMemcpyAsync((char*)keys_out + g0 * L.key_bytes, (char*)kcur + g0 * L.key_bytes,
+                                         (size_t)gn * L.key_bytes, cudaMemcpyDeviceToDevice, stream));
+                ETB_CUDA(cudaMemcpyAsync(vals_out + g0, vcur + g0, (size_t)gn * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
+            }
+            // CUB radix sort launches: histogram + exclusive sum + one onesweep pass per 8 key bits
+            launch_counter() += 2 + (sort_bits + 7) / 8;
+        }
+        keys[0] = keys_out;
+        if (L.key_bytes == 4) {
+            if (int32_t st = select_heads<uint32_t>(tiles, (const uint32_t*)keys[0], vals_out, recs, nnz, L.n_total, stream)) return st;
+        } else {
+            if (int32_t st = select_heads<uint64_t>(tiles, (const uint64_t*)keys[0], vals_out, recs, nnz, L.n_total, stream)) return st;
+        }
+        vals[0] = vals_out;
     }
     if (view) {
         view->keys = keys[0];
