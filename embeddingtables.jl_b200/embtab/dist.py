@@ -218,6 +218,38 @@ class ShardedEnsemble:
                                               C.c_void_p(current_stream_ptr())))
         self._barrier()
 
+    def distribute_indices(self, I_local: DeviceArray, wire_dtype=None):
+        """Data-parallel input: `I_local` holds MY samples' indices for ALL tables,
+        (bag, my_cols, T_total) [or (my_cols, T_total) for non-reducing lookups].  One all-to-all sends
+        each owner the slices of its tables; returns the list forward()/backward() expect: for each of
+        MY tables the (bag, B_global) [or (B_global,)] indices of the global batch.
+        `wire_dtype=np.int32` halves the bytes on the wire (the kernels take int32 indices natively)."""
+        p = self.plan
+        reducing = I_local.ndim == 3
+        bag = I_local.shape[0] if reducing else 1
+        assert I_local.shape[-1] == len(p.dims) and I_local.shape[-2] == p.my_cols and I_local.is_dense
+        n_local = int(np.prod(I_local.shape))
+        src = I_local.buf[I_local.offset:I_local.offset + n_local]
+        if wire_dtype is not None and np.dtype(wire_dtype) != I_local.dtype:
+            src = src.to(torch.int32 if np.dtype(wire_dtype) == np.int32 else torch.int64)
+        t_mine = len(p.my_tables)
+        send_splits = [bag * p.my_cols * (p.thi[q] - p.tlo[q]) for q in range(p.world)]  # last-dim slices are contiguous
+        recv_splits = [bag * p.cols[q] * t_mine for q in range(p.world)]
+        recv = torch.empty(sum(recv_splits), dtype=src.dtype, device=src.device)
+        exchange(recv, src, recv_splits, send_splits, self.group)
+        # received block of peer q is [table][q's columns][bag]; tables want [all columns][bag] each
+        glob = torch.empty(t_mine * bag * p.batch_global, dtype=src.dtype, device=src.device)
+        gv = glob.view(t_mine, p.batch_global * bag)
+        off = 0
+        for q in range(p.world):
+            if p.cols[q]:
+                gv[:, bag * p.clo[q]:bag * p.chi[q]] = recv[off:off + recv_splits[q]].view(t_mine, bag * p.cols[q])
+            off += recv_splits[q]
+        np_dtype = np.dtype(np.int32) if glob.dtype == torch.int32 else np.dtype(np.int64)
+        shape = (bag, p.batch_global) if reducing else (p.batch_global,)
+        per = bag * p.batch_global
+        return [DeviceArray(glob, shape, t * per, None, np_dtype) for t in range(t_mine)]
+
     def forward(self, I, out: DeviceArray = None) -> DeviceArray:
         p = self.plan
         Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else

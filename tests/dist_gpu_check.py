@@ -51,6 +51,17 @@ for fused in (False, True):     # NCCL all-to-all + pack/unpack, then NVLink pee
     torch.cuda.synchronize()
     dist.barrier()
     ens.close()
+# data-parallel input: every rank starts with ITS samples' indices for all tables
+ens = ShardedEnsemble([E.SimpleEmbedding(base[t].copy()) for t in mine], plan)
+I_all = np.stack(I, axis=2)                                             # (bag, batch, T)
+for wire in (None, np.int32):
+    mine_I = ens.distribute_indices(E.DeviceArray.from_numpy(I_all[:, plan.clo[rank]:plan.chi[rank], :]), wire_dtype=wire)
+    for k, t in enumerate(mine):
+        assert np.array_equal(mine_I[k].numpy(), I[t]), f"index distribution differs (wire={wire})"
+    got = ens.forward(mine_I).numpy()
+    assert np.array_equal(got[prepend:], ref_out.numpy()[prepend:, plan.clo[rank]:plan.chi[rank]])
+torch.cuda.synchronize()
+dist.barrier()
 if rank == 0:
     print("dist check ok", world)
 dist.destroy_process_group()
