@@ -331,8 +331,14 @@ def run_ours(args):
         "index(make_pairs+radix sort+select)": {"ms": index_ms},
     }
     dom = "pooled_kernel" if fwd_ms >= upd_ms else "sgd_update_kernel"
+    traffic = None      # DRAM bytes per launch of that kernel from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")) as f:
+            traffic = json.load(f)["kernels"][dom]["dram_bytes"] if args.dist == "uniform" else None
+    except Exception:
+        traffic = None
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
-            "frac": kernels[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+            "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "frac_of_nominal_8TBs": kernels[dom]["gbs"] / 8000.0}
 
     cpu = cpu_reference_arm(steps=2, warmup=1, dist=args.dist) if not args.no_cpu_baseline else None

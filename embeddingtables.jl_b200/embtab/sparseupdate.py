@@ -157,7 +157,9 @@ def prefetch_index(indexer: Indexer, tables, indices):
     dev = torch.cuda.current_device()
     side = _SIDE_STREAM.get(dev)
     if side is None:
-        side = _SIDE_STREAM[dev] = torch.cuda.Stream()
+        # high priority: the many small sort kernels get SM slots as soon as CTAs of a concurrent
+        # bandwidth-bound kernel (the forward) retire, instead of queueing behind its whole grid
+        side = _SIDE_STREAM[dev] = torch.cuda.Stream(priority=-1)
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         index_(indexer, tables, [_IndicesOnly(t, i) for t, i in zip(tables, Is)])
