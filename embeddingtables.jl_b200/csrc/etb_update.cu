@@ -447,7 +447,6 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
     const T eta = (T)P.eta;  // convert(eltype(table), opt.eta), reference src/sparseupdate.jl:173
-    const bool fma = P.fma != 0;
 
     int64_t s_begin = 0, s_end = nnz;
     if (P.num_splits > 0) {  // cumulative has nnz+1 entries; split_size = cdiv(nnz+1, num_splits)
@@ -488,7 +487,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
             prefetch_row_l2(m.d0, (uint32_t)nvec * VB);
         }
         s_meta[wbase + r * 32 + lane] = m;
-        s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0, 0};
+        s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0, (int32_t)md.table.pad};
     }
     __syncwarp();
 
@@ -532,7 +531,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                                     V out;
 #pragma unroll
                                     for (int e = 0; e < V::NE; ++e)
-                                        out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[p].e[e], eta, fma);
+                                        out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[p].e[e], eta, m2.pad != 0);
                                     st_plain<VB>(row + vi[p], &out);
                                 }
                             }
@@ -590,11 +589,10 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
         m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
         s_meta[threadIdx.x] = m;
-        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, 0};
+        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, (int32_t)md.table.pad};
     }
     __syncwarp();
     const T eta = (T)P.eta;
-    const bool fma = P.fma != 0;
 #pragma unroll 1
     for (int k0 = 0; k0 < G; k0 += UB) {
         V old[UB][VPL], acc[UB][VPL];
@@ -635,7 +633,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                 for (int p = 0; p < VPL; ++p) {
                     V out;
 #pragma unroll
-                    for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[u][p].e[e], eta, fma);
+                    for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
                     st_plain<VB>(row + p * G * VB, &out);
                 }
             }
@@ -658,7 +656,6 @@ medium_buckets_kernel(const __grid_constant__ UpdParams P) {
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
     const T eta = (T)P.eta;
-    const bool fma = P.fma != 0;
     const uint32_t groups_total = gridDim.x * (kUThreads / G);
     for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_medium; i += groups_total) {
         const uint32_t b = P.mediums[i];
@@ -683,7 +680,7 @@ medium_buckets_kernel(const __grid_constant__ UpdParams P) {
                 if (pass0 + gl + p * G < nvec) {
                     V out;
 #pragma unroll
-                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, fma);
+                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
                     st_plain<VB>(row + vi[p], &out);
                 }
             }
@@ -742,7 +739,6 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
     const uint32_t n_long = P.counters->n_long;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
     const T eta = (T)P.eta;
-    const bool fma = P.fma != 0;
     const uint32_t groups_total = gridDim.x * (kUThreads / G);
     for (uint32_t j = blockIdx.x * (kUThreads / G) + threadIdx.x / G; j < n_long; j += groups_total) {
         const LongRec lr = P.longs[j];
@@ -781,7 +777,7 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
                 if (pass0 + gl + p * G < nvec) {
                     V out;
 #pragma unroll
-                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, fma);
+                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
                     st_plain<VB>(row + vi[p], &out);
                 }
             }
@@ -1049,6 +1045,7 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
             const etb_update_item& it = items[i0 + n];
             UpdDesc& d = P.item[n];
             d.table = make_dev_table(it.table);
+            d.table.pad = ((flags | it.flags) & ETB_UPDATE_FMA) ? 1u : 0u;  // per-table epilogue
             d.delta = (const char*)it.delta;
             d.ld_delta_bytes = it.ld_delta * (int64_t)elt_bytes(it.table.elt);
             ++n;

@@ -35,7 +35,7 @@ class LookupItem(C.Structure):
 class UpdateItem(C.Structure):
     _fields_ = [("table", Table), ("delta", C.c_void_p), ("ld_delta", C.c_int64),
                 ("idx", C.c_void_p), ("batch", C.c_int64), ("bag", C.c_int64),
-                ("ld_idx", C.c_int64), ("idx_elt", C.c_int32), ("reserved", C.c_int32)]
+                ("ld_idx", C.c_int64), ("idx_elt", C.c_int32), ("flags", C.c_int32)]
 
 
 class IndexView(C.Structure):

@@ -47,7 +47,8 @@ def _update_item(table, grad: SparseEmbeddingUpdate) -> _lib.UpdateItem:
         raise TypeError(f"delta eltype {d.dtype} != table eltype {table.dtype}")
     if d.shape[0] < featuresize(table) or d.shape[1] < batch:
         raise ValueError(f"delta {d.shape} too small for {featuresize(table)} x {batch}")
-    return _lib.UpdateItem(table.descriptor(), d.ptr, d.ld, I.ptr, batch, bag, ld_idx, I.elt, 0)
+    return _lib.UpdateItem(table.descriptor(), d.ptr, d.ld, I.ptr, batch, bag, ld_idx, I.elt,
+                           _flags(table) & _lib.UPDATE_FMA)   # the epilogue is a per-table choice
 
 
 def uncompress(x: SparseEmbeddingUpdate, dstcols=None, maxindices=None) -> DeviceArray:
@@ -219,13 +220,9 @@ def _apply(tables, grads, indexer, eta):
         view.num_splits, view.this_split = indexer.num_splits, indexer.this_split
     else:
         base, view = indexer, indexer.view
-    flags = {_flags(t) for t in tables}
+    flags = _lib.UPDATE_SPLIT_LONG if _ORDER["mode"] == "split" else 0   # FMA travels per item
     stream = C.c_void_p(current_stream_ptr())
-    if len(flags) == 1:
-        _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(tables), float(eta), flags.pop(), stream))
-    else:  # mixed Static/Dynamic ensemble: the epilogue differs per table -> would need per-item flags
-        raise _lib.EmbTabError("ensemble update! needs tables that share the update kernel class "
-                               "(all Static f32 dim<=128, or none); index/update them separately")
+    _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(tables), float(eta), flags, stream))
 
 
 def update_table_(table, update: SparseEmbeddingUpdate, indexer, alpha, nontemporal=True, *args):

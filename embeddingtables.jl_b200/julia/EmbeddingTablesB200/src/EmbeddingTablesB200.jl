@@ -47,7 +47,7 @@ struct EtbUpdateItem         # etb_update_item
     bag::Int64
     ld_idx::Int64
     idx_elt::Int32
-    reserved::Int32
+    flags::Int32             # per-table ETB_UPDATE_FMA
 end
 const ETB_UPDATE_FMA = Int32(1)
 const ETB_UPDATE_SPLIT_LONG = Int32(2)
@@ -273,16 +273,18 @@ mutable struct Indexer
     Indexer() = new(nothing)
 end
 
+# the reference's @generated dispatch (src/sparseupdate.jl:131-154): FMA epilogue for Static{N} Float32
+# tables with N*4 <= 512 and N % 16 == 0 -- a per-table flag
 update_flags(::AbstractEmbeddingTable{Static{N},Float32}) where {N} =
-    (N * 4 <= 512 && N % 16 == 0) ? (ETB_UPDATE_FMA | ETB_UPDATE_SPLIT_LONG) : ETB_UPDATE_SPLIT_LONG
-update_flags(::AbstractEmbeddingTable) = ETB_UPDATE_SPLIT_LONG
+    (N * 4 <= 512 && N % 16 == 0) ? ETB_UPDATE_FMA : Int32(0)
+update_flags(::AbstractEmbeddingTable) = Int32(0)
 
 function update_item(table::AbstractEmbeddingTable, g::SparseEmbeddingUpdate)
     desc, keep = descriptor(table)
     I = todevice(g.indices)
     bag = I.isvec ? 0 : size(I.data, 1)
     return EtbUpdateItem(desc, pointer(g.delta), g.delta.ld, pointer(I.data), _trailing_size(I), bag,
-                         I.isvec ? 0 : I.data.ld, etb_elt(Int64), 0), (keep, I)
+                         I.isvec ? 0 : I.data.ld, etb_elt(Int64), update_flags(table)), (keep, I)
 end
 
 function update_many!(eta, tables, grads, indexer::Indexer)
@@ -297,7 +299,7 @@ function update_many!(eta, tables, grads, indexer::Indexer)
     GC.@preserve items pairs tables grads check(ccall((:etb_index_and_update, libembtab[]), Int32,
         (Ptr{Cvoid}, Csize_t, Ptr{EtbUpdateItem}, Int32, Float64, Int32, Ptr{Cvoid}),
         pointer(indexer.workspace), length(indexer.workspace), items, length(items), Float64(eta),
-        update_flags(first(tables)), C_NULL))
+        ETB_UPDATE_SPLIT_LONG, C_NULL))
     check(ccall((:etb_stream_sync, libembtab[]), Int32, (Ptr{Cvoid},), C_NULL))
     return nothing
 end

@@ -129,7 +129,8 @@ typedef struct etb_update_item {
     int64_t bag;     /* 0 = vector of indices (one per delta column) */
     int64_t ld_idx;
     int32_t idx_elt;
-    int32_t reserved;
+    int32_t flags;   /* per-table ETB_UPDATE_FMA (OR-ed with the call's flags): the reference picks the
+                      * epilogue per table type (src/sparseupdate.jl:131-154), so an ensemble may mix them */
 } etb_update_item;
 
 /* ---------------------------------------------------------------- runtime ------------- */

@@ -24,15 +24,19 @@ I = [rng.integers(1, nrows + 1, (bag, batch)) for _ in dims]
 total = prepend + sum(dims)
 delta = rng.standard_normal((total, batch)).astype(np.float32)
 
-# single-GPU reference on this rank
-ref_tables = [E.SimpleEmbedding(b.copy()) for b in base]
+def make_table(t):              # C4 uses SplitEmbedding tables: every other table is chunked (ragged last chunk)
+    return E.SplitEmbedding(base[t].copy(), 200) if t % 2 else E.SimpleEmbedding(base[t].copy())
+
+
+# single-GPU reference on this rank (same table types: the update epilogue is chosen per table type)
+ref_tables = [make_table(t) for t in range(len(base))]
 ref_out, back = E.pullback(E.maplookup, E.PreallocationStrategy(prepend), ref_tables, I)
 E.update_(E.Descent(0.1), ref_tables, back(delta)[2], [E.Indexer()])
 
 plan = ShardPlan(dims, world, rank, prepend, batch)
 mine = list(plan.my_tables)
 for fused in (False, True):     # NCCL all-to-all + pack/unpack, then NVLink peer stores
-    ens = ShardedEnsemble([E.SimpleEmbedding(base[t].copy()) for t in mine], plan, fused=fused)
+    ens = ShardedEnsemble([make_table(t) for t in mine], plan, fused=fused)
     ens.out.fill(-5.0)
     torch.cuda.synchronize()
     dist.barrier()

@@ -302,3 +302,25 @@ def test_prefetch_index_overlapped(E, O):
     ref = O.Table(base[0].copy(order="F"), static=True)
     O.update(ref, deltas[0], I[:, :, 0], 0.3)
     assert np.array_equal(t1.to_numpy(), ref.data)
+
+
+def test_mixed_static_dynamic_ensemble(E, O):
+    # the FMA-vs-two-roundings epilogue is a per-table choice (reference @generated dispatch): an ensemble
+    # may mix Static (fma) and Dynamic (two roundings) tables in one call
+    rng = np.random.default_rng(31)
+    base = [rng.standard_normal((64, 200)).astype(np.float32) for _ in range(4)]
+    statics = [True, False, True, False]
+    tables = [E.SimpleEmbedding(b.copy(), E.Static(64) if st else None) for b, st in zip(base, statics)]
+    I = rng.integers(1, 201, (5, 150, 4))
+    deltas = [rng.standard_normal((64, 150)).astype(np.float32) for _ in range(4)]
+    grads = [E.SparseEmbeddingUpdate(t.lookup_type, d, I[:, :, k]) for k, (t, d) in enumerate(zip(tables, deltas))]
+    E.update_(E.Descent(0.7), tables, grads, [E.Indexer()])
+    differ = 0
+    for k, (t, b, d, st) in enumerate(zip(tables, base, deltas, statics)):
+        ref = O.Table(b.copy(order="F"), static=st)
+        O.update(ref, d, I[:, :, k], 0.7)
+        assert np.array_equal(t.to_numpy(), ref.data)
+        other = O.Table(b.copy(order="F"), static=not st)
+        O.update(other, d, I[:, :, k], 0.7)
+        differ += int(not np.array_equal(other.data, ref.data))
+    assert differ > 0   # the two epilogues really round differently, so the test can tell them apart

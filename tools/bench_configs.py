@@ -187,11 +187,45 @@ def config_c5(fh, quick=False):
         torch.cuda.empty_cache()
 
 
+def config_c4local(fh):
+    """C4's per-GPU share on one GPU: 8 SplitEmbedding tables 128 x 5M f32 (cols_per_shard 1 048 576: 5 chunks,
+    last ragged), bag 32, global batch 131 072: fused pooled lookup into the (8*128) x B matrix + ensemble update!.
+    (The exchange itself is measured by bench.py --gpus 8 on C2; this isolates chunked-table addressing.)"""
+    nt, dim, nrows, shard, bag = 8, 128, 5_000_000, 1_048_576, 32
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    for kind in ("split", "simple"):
+        tables = []
+        for _ in range(nt):
+            if kind == "split":
+                chunks = [E.DeviceArray(torch.rand(dim * (min(s + shard, nrows) - s), device="cuda", generator=gen),
+                                        (dim, min(s + shard, nrows) - s)) for s in range(0, nrows, shard)]
+                tables.append(E.SplitEmbedding(None, shard, _chunks=chunks, _lookup_type=E.Static(dim), _dtype=np.float32, _fs=dim))
+            else:
+                tables.append(E.SimpleEmbedding(E.DeviceArray(torch.rand(dim * nrows, device="cuda", generator=gen), (dim, nrows)), E.Static(dim)))
+        for batch in (16384, 131072):
+            I = E.DeviceArray(torch.randint(1, nrows + 1, (bag * batch * nt,), device="cuda", dtype=torch.int64), (bag, batch, nt))
+            Is = list(E.colwrap(I))
+            out = E.DeviceArray.empty((nt * dim, batch))
+            delta = E.DeviceArray(torch.randn(nt * dim * batch, device="cuda"), (nt * dim, batch))
+            grads = [E.SparseEmbeddingUpdate(E.Static(dim), delta.rows(k * dim, (k + 1) * dim), i) for k, i in enumerate(Is)]
+            indexer, opt = E.Indexer(), E.Descent(0.01)
+            t_f = timeit_graph(lambda: E.maplookup_(E.PreallocationStrategy(0), out, tables, I), iters=10, warmup=2)
+            t_u = timeit(lambda: E.update_(opt, tables, grads, [indexer]), iters=10, warmup=2)
+            fb = nt * batch * (bag * (8 + dim * 4) + dim * 4)
+            emit({"config": "C4-local", "tables": kind, "shape": f"{nt} x (128 x 5M), bag {bag}, batch {batch}",
+                  "fwd_ms": t_f, "fwd_gbs": fb / t_f / 1e6, "fwd_frac_of_measured_peak": fb / t_f / 1e6 / PEAK,
+                  "fwd_lookups_per_sec": nt * batch * bag / (t_f * 1e-3), "update_ms": t_u,
+                  "step_lookups_per_sec": nt * batch * bag / ((t_f + t_u) * 1e-3)}, fh)
+            del I, out, delta, grads, indexer
+        del tables
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c1", "c3", "c5", "c5quick"])
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4local", "c5", "c5quick"])
     ap.add_argument("--out")
     a = ap.parse_args()
     E._lib.check(E.lib().etb_init(0))
     fh = open(a.out, "a") if a.out else None
-    {"c1": config_c1, "c3": config_c3, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)
+    {"c1": config_c1, "c3": config_c3, "c4local": config_c4local, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)
