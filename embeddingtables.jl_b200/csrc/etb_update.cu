@@ -65,22 +65,23 @@ struct alignas(16) BucketRec {
 };
 
 // Bucket classes of the update: SHORT (<= kShortMax members) finish inside the main kernel; MEDIUM
-// (kShortMax < members <= kLongThreshold, and every larger bucket in strict mode) go to a worklist
-// and are reduced strictly in order by medium_buckets_kernel with 8 rows in flight; LONG
-// (> kLongThreshold, ETB_UPDATE_SPLIT_LONG only) are reduced as kLongChunk-member chunks combined in
-// chunk order.
+// (kShortMax < members <= kLongThreshold, and every larger bucket in strict mode) become tasks of
+// bucket_tasks_kernel and are reduced strictly in order with 8 rows in flight; LONG (> kLongThreshold,
+// ETB_UPDATE_SPLIT_LONG only) are cut into kLongChunk-member chunk tasks whose partial rows
+// long_combine_kernel adds in a fixed order.
 constexpr int kShortMax = 4;
 constexpr int kLongThreshold = 128;  // buckets with more members than this are "long"
 constexpr int kLongChunk = 128;      // members per partial sum
-struct LongCounters { uint32_t n_long, n_chunks, n_medium, pad; };
+struct LongCounters { uint32_t n_long, n_chunks /* task cursor */, n_partials, pad; };
 struct LongRec { uint32_t bucket, chunk_base, nchunks, pad; };
-struct ChunkRec { uint32_t long_id, chunk; };
+struct ChunkRec { uint32_t long_id, chunk; };  // long_id == kMediumTask: a MEDIUM bucket, chunk = its bucket index
+constexpr uint32_t kMediumTask = 0xffffffffu;
 
 struct IndexLayout {
     int64_t n_total;
     int32_t row_bits, slot_bits, key_bytes;
-    size_t max_long, max_chunks, max_medium, partial_pitch;
-    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_tiles, off_counters, off_long, off_chunks, off_medium, off_partials,
+    size_t max_long, max_chunks, max_medium, max_tasks, partial_pitch;
+    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_tiles, off_counters, off_long, off_chunks, off_partials,
         off_temp, temp_bytes, total;
 };
 
@@ -252,8 +253,9 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     L.key_bytes = (L.row_bits + L.slot_bits <= 32) ? 4 : 8;
     const size_t n = (size_t)std::max<int64_t>(n_total, 1);
     L.max_long = n / kLongThreshold + 1;
-    L.max_chunks = n / kLongChunk + L.max_long;
     L.max_medium = n / (kShortMax + 1) + 1;
+    L.max_chunks = n / kLongChunk + L.max_long;  // partial rows
+    L.max_tasks = L.max_chunks + L.max_medium;    // task list = long chunks + medium buckets
     L.partial_pitch = align_up(max_row_bytes, 16);
     size_t off = 0;
     for (int b = 0; b < 2; ++b) { L.off_keys[b] = off; off = align_up(off + n * L.key_bytes); }
@@ -263,8 +265,7 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     L.off_tiles = off; off = align_up(off + ((n + kSelTile - 1) / kSelTile + 1) * sizeof(uint32_t));
     L.off_counters = off; off = align_up(off + sizeof(LongCounters));
     L.off_long = off; off = align_up(off + L.max_long * sizeof(LongRec));
-    L.off_chunks = off; off = align_up(off + L.max_chunks * sizeof(ChunkRec));
-    L.off_medium = off; off = align_up(off + L.max_medium * sizeof(uint32_t));
+    L.off_chunks = off; off = align_up(off + L.max_tasks * sizeof(ChunkRec));
     L.off_partials = off; off = align_up(off + L.max_chunks * L.partial_pitch);
     // CUB temp storage of the radix sort
     size_t t_sort = 0;
@@ -330,7 +331,6 @@ struct UpdParams {
     LongCounters* counters;
     LongRec* longs;
     ChunkRec* chunks;
-    uint32_t* mediums;
     char* partials;
     int64_t partial_pitch;
     int64_t n_total;
@@ -412,9 +412,10 @@ __device__ __noinline__ void register_long_bucket(LongCounters* counters, LongRe
                                                   uint32_t bucket, int cnt) {
     const uint32_t nch = (uint32_t)((cnt + kLongChunk - 1) / kLongChunk);
     const uint32_t j = atomicAdd(&counters->n_long, 1u);
-    const uint32_t cb = atomicAdd(&counters->n_chunks, nch);
-    longs[j] = LongRec{bucket, cb, nch, 0u};
-    for (uint32_t c = 0; c < nch; ++c) chunks[cb + c] = ChunkRec{j, c};
+    const uint32_t pb = atomicAdd(&counters->n_partials, nch);  // rows of the partial-sum buffer
+    const uint32_t tb = atomicAdd(&counters->n_chunks, nch);    // slots of the task list
+    longs[j] = LongRec{bucket, pb, nch, 0u};
+    for (uint32_t c = 0; c < nch; ++c) chunks[tb + c] = ChunkRec{j, c};
 }
 
 struct alignas(16) TileMeta {
@@ -474,7 +475,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         int cnt = mine ? (int)(stop - start) : 0;
         if (cnt > kShortMax) {
             if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
-            else P.mediums[atomicAdd(&P.counters->n_medium, 1u)] = (uint32_t)s;
+            else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
         }
         TileMeta m;
@@ -581,7 +582,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         int cnt = mine ? (int)(stop - (int64_t)raw.x) : 0;
         if (cnt > kShortMax) {
             if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
-            else P.mediums[atomicAdd(&P.counters->n_medium, 1u)] = (uint32_t)s;
+            else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
         }
         const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
@@ -641,28 +642,42 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
     }
 }
 
-// MEDIUM buckets: one group per bucket, accumulated from zero strictly in occurrence order with 8
-// rows in flight -- the reference's order exactly, just with the loads issued ahead of the adds.
+// Task kernel: MEDIUM buckets and the chunks of LONG buckets are the same job -- sum a run of members
+// strictly in occurrence order from zero, 8 rows in flight -- so they share one worklist and one
+// launch (they overlap instead of running back to back).  A medium task finishes its table row; a
+// chunk task writes its partial row.
 template <typename T, int VB, int VPL>
-__global__ void __launch_bounds__(kUThreads)
-medium_buckets_kernel(const __grid_constant__ UpdParams P) {
+__global__ void __launch_bounds__(kUThreads, 2)  // up to 128 registers: a spill of loaded rows serialises the loads
+bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
     using V = Vec<T, VB>;
     const int G = P.G, nvec = P.nvec;
     const int lane = threadIdx.x & 31;
     const int gl = lane & (G - 1);
     const unsigned gmask = group_mask(G, lane);
-    const uint32_t n_medium = P.counters->n_medium;
+    const uint32_t n_tasks = P.counters->n_chunks;
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
     const T eta = (T)P.eta;
     const uint32_t groups_total = gridDim.x * (kUThreads / G);
-    for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_medium; i += groups_total) {
-        const uint32_t b = P.mediums[i];
-        const BucketRec rec = P.recs[b];
-        const int64_t stop = ((int64_t)b + 1 < nnz) ? (int64_t)P.recs[b + 1].start : P.n_total;
+    for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_tasks; i += groups_total) {
+        const ChunkRec cr = P.chunks[i];
+        const bool medium = cr.long_id == kMediumTask;
+        uint32_t bucket, pbase = 0;
+        if (medium) {
+            bucket = cr.chunk;
+        } else {
+            const LongRec lr = P.longs[cr.long_id];
+            bucket = lr.bucket;
+            pbase = lr.chunk_base;
+        }
+        const BucketRec rec = P.recs[bucket];
+        const int64_t stop_all = ((int64_t)bucket + 1 < nnz) ? (int64_t)P.recs[bucket + 1].start : P.n_total;
+        const int64_t a = medium ? (int64_t)rec.start : (int64_t)rec.start + (int64_t)cr.chunk * kLongChunk;
+        const int64_t b = medium ? stop_all : min(a + kLongChunk, stop_all);
         const UpdDesc& d = P.item[(int)(rec.key >> P.row_bits) - P.slot0];
         char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
+        char* part = P.partials + (int64_t)(pbase + cr.chunk) * P.partial_pitch;
         for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
             int vi[VPL];
 #pragma unroll
@@ -670,47 +685,53 @@ medium_buckets_kernel(const __grid_constant__ UpdParams P) {
             V old[VPL], acc[VPL];
 #pragma unroll
             for (int p = 0; p < VPL; ++p) {
-                ld_plain<VB>(&old[p], row + vi[p]);
+                if (medium) ld_plain<VB>(&old[p], row + vi[p]);
 #pragma unroll
                 for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
             }
-            accumulate_members<T, VB, VPL, U>(acc, d, P.map, (int64_t)rec.start, stop, vi, G, gl, lane, gmask);
+            accumulate_members<T, VB, VPL, U>(acc, d, P.map, a, b, vi, G, gl, lane, gmask);
 #pragma unroll
             for (int p = 0; p < VPL; ++p) {
                 if (pass0 + gl + p * G < nvec) {
-                    V out;
+                    if (medium) {
+                        V out;
 #pragma unroll
-                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
-                    st_plain<VB>(row + vi[p], &out);
+                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
+                        st_plain<VB>(row + vi[p], &out);
+                    } else {
+                        st_plain<VB>(part + vi[p], &acc[p]);
+                    }
                 }
             }
         }
     }
 }
 
-// ETB_UPDATE_SPLIT_LONG, phase A: one group per (long bucket, chunk): the chunk's members summed
-// strictly in order from zero into a partial row.
+// LONG buckets, phase B: one CTA per long bucket.  Its kUThreads/G groups each add a contiguous range of
+// the bucket's partial rows in chunk order (8 in flight); the group sums are then added in group order
+// through shared memory and the epilogue is applied.  The split depends only on the chunk count:
+// deterministic.
 template <typename T, int VB, int VPL>
 __global__ void __launch_bounds__(kUThreads)
-long_partials_kernel(const __grid_constant__ UpdParams P) {
+long_combine_kernel(const __grid_constant__ UpdParams P) {
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
     using V = Vec<T, VB>;
+    __shared__ __align__(16) char s_sum[kUThreads * VPL * VB];  // [group][G * VPL vectors]
     const int G = P.G, nvec = P.nvec;
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (G - 1);
-    const unsigned gmask = group_mask(G, lane);
-    const uint32_t n_chunks = P.counters->n_chunks;
-    const int64_t nnz = *P.nnz;
-    const uint32_t groups_total = gridDim.x * (kUThreads / G);
-    for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_chunks; i += groups_total) {
-        const ChunkRec cr = P.chunks[i];
-        const LongRec lr = P.longs[cr.long_id];
+    const int gl = threadIdx.x & (G - 1);
+    const int grp = threadIdx.x / G, ngroups = kUThreads / G;
+    const uint32_t n_long = P.counters->n_long;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    const T eta = (T)P.eta;
+    for (uint32_t j = blockIdx.x; j < n_long; j += gridDim.x) {
+        const LongRec lr = P.longs[j];
         const BucketRec rec = P.recs[lr.bucket];
-        const int64_t stop_all = ((int64_t)lr.bucket + 1 < nnz) ? (int64_t)P.recs[lr.bucket + 1].start : P.n_total;
-        const int64_t a = (int64_t)rec.start + (int64_t)cr.chunk * kLongChunk;
-        const int64_t b = min(a + kLongChunk, stop_all);
         const UpdDesc& d = P.item[(int)(rec.key >> P.row_bits) - P.slot0];
-        char* out = P.partials + (int64_t)(lr.chunk_base + cr.chunk) * P.partial_pitch;
+        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
+        const char* part = P.partials + (int64_t)lr.chunk_base * P.partial_pitch;
+        const uint32_t per = (lr.nchunks + ngroups - 1) / ngroups;
+        const uint32_t c_lo = min((uint32_t)grp * per, lr.nchunks), c_hi = min(c_lo + per, lr.nchunks);
+        const int used_groups = (int)((lr.nchunks + per - 1) / per);
         for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
             int vi[VPL];
 #pragma unroll
@@ -720,67 +741,43 @@ long_partials_kernel(const __grid_constant__ UpdParams P) {
             for (int p = 0; p < VPL; ++p)
 #pragma unroll
                 for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
-            accumulate_members<T, VB, VPL, U>(acc, d, P.map, a, b, vi, G, gl, lane, gmask);
-#pragma unroll
-            for (int p = 0; p < VPL; ++p)
-                if (pass0 + gl + p * G < nvec) st_plain<VB>(out + vi[p], &acc[p]);
-        }
-    }
-}
-
-// phase B: one group per long bucket: partials added in chunk order from zero, then the epilogue.
-template <typename T, int VB, int VPL>
-__global__ void __launch_bounds__(kUThreads)
-long_combine_kernel(const __grid_constant__ UpdParams P) {
-    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
-    using V = Vec<T, VB>;
-    const int G = P.G, nvec = P.nvec;
-    const int gl = threadIdx.x & (G - 1);
-    const uint32_t n_long = P.counters->n_long;
-    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
-    const T eta = (T)P.eta;
-    const uint32_t groups_total = gridDim.x * (kUThreads / G);
-    for (uint32_t j = blockIdx.x * (kUThreads / G) + threadIdx.x / G; j < n_long; j += groups_total) {
-        const LongRec lr = P.longs[j];
-        const BucketRec rec = P.recs[lr.bucket];
-        const UpdDesc& d = P.item[(int)(rec.key >> P.row_bits) - P.slot0];
-        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
-        const char* part = P.partials + (int64_t)lr.chunk_base * P.partial_pitch;
-        for (int pass0 = 0; pass0 < nvec; pass0 += G * VPL) {
-            int vi[VPL];
-#pragma unroll
-            for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
-            V old[VPL], acc[VPL];
-#pragma unroll
-            for (int p = 0; p < VPL; ++p) {
-                ld_plain<VB>(&old[p], row + vi[p]);
-#pragma unroll
-                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
-            }
-            for (uint32_t c0 = 0; c0 < lr.nchunks; c0 += U) {
+            for (uint32_t c0 = c_lo; c0 < c_hi; c0 += U) {
                 V v[U][VPL];
 #pragma unroll
                 for (int w = 0; w < U; ++w)
-                    if (c0 + w < lr.nchunks)
+                    if (c0 + w < c_hi)
 #pragma unroll
                         for (int p = 0; p < VPL; ++p) ld_plain<VB>(&v[w][p], part + (int64_t)(c0 + w) * P.partial_pitch + vi[p]);
 #pragma unroll
                 for (int w = 0; w < U; ++w)
-                    if (c0 + w < lr.nchunks)
+                    if (c0 + w < c_hi)
 #pragma unroll
                         for (int p = 0; p < VPL; ++p)
 #pragma unroll
                             for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
             }
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) {
-                if (pass0 + gl + p * G < nvec) {
-                    V out;
+            for (int p = 0; p < VPL; ++p) *(V*)(s_sum + ((size_t)(grp * VPL + p) * G + gl) * VB) = acc[p];
+            __syncthreads();
+            if (grp == 0) {
 #pragma unroll
-                    for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
-                    st_plain<VB>(row + vi[p], &out);
+                for (int p = 0; p < VPL; ++p) {
+                    V old, tot = *(const V*)(s_sum + ((size_t)p * G + gl) * VB);
+                    if (pass0 + gl + p * G < nvec) ld_plain<VB>(&old, row + vi[p]);
+                    for (int g2 = 1; g2 < used_groups; ++g2) {  // groups without chunks are skipped (no 0 + -0)
+                        const V v = *(const V*)(s_sum + ((size_t)(g2 * VPL + p) * G + gl) * VB);
+#pragma unroll
+                        for (int k = 0; k < V::NE; ++k) tot.e[k] = tot.e[k] + v.e[k];
+                    }
+                    if (pass0 + gl + p * G < nvec) {
+                        V out;
+#pragma unroll
+                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old.e[k], tot.e[k], eta, d.table.pad != 0);
+                        st_plain<VB>(row + vi[p], &out);
+                    }
                 }
             }
+            __syncthreads();
         }
     }
 }
@@ -818,13 +815,12 @@ static UpdClass classify_update(const etb_update_item& it) {
     return c;
 }
 
-enum { kKernelMain = 0, kKernelPartials = 1, kKernelCombine = 2, kKernelMedium = 3 };
+enum { kKernelMain = 0, kKernelTasks = 1, kKernelCombine = 2 };
 
 template <typename T, int VB, int VPL>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain) sgd_update_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
-    else if (which == kKernelMedium) medium_buckets_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
-    else if (which == kKernelPartials) long_partials_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
+    else if (which == kKernelTasks) bucket_tasks_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
     else long_combine_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
 }
 
@@ -1026,7 +1022,6 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
     P.counters = (LongCounters*)scratch;
     P.longs = (LongRec*)(scratch + (L.off_long - L.off_counters));
     P.chunks = (ChunkRec*)(scratch + (L.off_chunks - L.off_counters));
-    P.mediums = (uint32_t*)(scratch + (L.off_medium - L.off_counters));
     P.partials = scratch + (L.off_partials - L.off_counters);
     P.partial_pitch = (int64_t)L.partial_pitch;
     P.n_total = view->n_total;
@@ -1060,19 +1055,15 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         launch_update(kKernelMain, c, grid, stream, P);
         ETB_LAUNCHED();
         const int64_t per_block = kUThreads / c.G;
-        if (view->n_total > kShortMax) {
-            const int64_t max_medium = view->n_total / (kShortMax + 1) + 1;
-            const int gridM = (int)std::min<int64_t>((max_medium + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
-            launch_update(kKernelMedium, c, gridM, stream, P);
+        if (view->n_total > kShortMax) {  // medium buckets + long-bucket chunks: one task kernel
+            const int64_t max_tasks = view->n_total / (kShortMax + 1) + 1;
+            const int gridT = (int)std::min<int64_t>((max_tasks + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
+            launch_update(kKernelTasks, c, gridT, stream, P);
             ETB_LAUNCHED();
         }
         if (P.split_long && view->n_total > kLongThreshold) {
-            const int64_t max_chunks = view->n_total / kLongChunk + 1;
-            const int gridA = (int)std::min<int64_t>((max_chunks + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
-            launch_update(kKernelPartials, c, gridA, stream, P);
-            ETB_LAUNCHED();
             const int64_t max_long = view->n_total / kLongThreshold + 1;
-            const int gridB = (int)std::min<int64_t>((max_long + per_block - 1) / per_block, (int64_t)kNumSMs * 4);
+            const int gridB = (int)std::min<int64_t>(max_long, (int64_t)kNumSMs * 4);  // one CTA per long bucket
             launch_update(kKernelCombine, c, gridB, stream, P);
             ETB_LAUNCHED();
         }
