@@ -240,7 +240,8 @@ def run_ours(args):
     # indices are uploaded on a copy stream while step k's result is downloaded (H2D and D2H use
     # different copy engines).  Within a step the dependency chain is kept: forward -> result on the
     # host -> cotangent from the host -> update.
-    copy_stream = torch.cuda.Stream()
+    copy_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    E2E_CHUNKS = 4
     I_buf = [I_dev, E.DeviceArray.empty((BAG, BATCH, NT), np.int64)]
     Is_buf = [Is, list(E.colwrap(I_buf[1]))]
     idx_ready = [None, None]
@@ -263,9 +264,17 @@ def run_ours(args):
         main.wait_event(idx_ready[slot])
         idx_ready[slot] = None
         E.prefetch_index(indexer, tables, Is_buf[slot])   # side stream: overlaps forward + PCIe copies
-        E.maplookup_(strategy, out_dev, tables, I_buf[slot])
+        # forward in E2E_CHUNKS column chunks: chunk c's result goes to the host (D2H stream) while chunk
+        # c+1 is being looked up
+        for c in range(E2E_CHUNKS):
+            c0, c1 = c * BATCH // E2E_CHUNKS, (c + 1) * BATCH // E2E_CHUNKS
+            E.maplookup_(strategy, out_dev.cols(c0, c1), tables, [i.cols(c0, c1) for i in Is_buf[slot]])
+            done = main.record_event()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                out_dev.cols(c0, c1).download(out_pinned[:, c0:c1])   # D2H: the step's result, chunk c
         upload_indices(1 - slot)                          # next step's indices, behind this step's D2H
-        out_dev.download(out_pinned)                      # D2H: the step's result (feature matrix)
+        main.wait_stream(d2h_stream)                      # the host has the whole feature matrix
         delta_dev.upload(delta_pinned)                    # H2D: the upstream cotangent
         slicer = E.Slicer(PREPEND + 1, 1, delta_dev)
         grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is_buf[slot]]

@@ -165,6 +165,7 @@ class DeviceArray:
     def download(self, host: np.ndarray) -> np.ndarray:
         """Asynchronous device->host copy on the current stream (synchronise before reading)."""
         assert self.is_dense and host.dtype == self.dtype and host.size == int(np.prod(self.shape))
+        assert host.flags.f_contiguous or host.flags.c_contiguous, "download target must be one contiguous block"
         _lib.check(_lib.lib().etb_memcpy_d2h(host.ctypes.data, self.ptr, host.nbytes, current_stream_ptr()))
         return host
 
