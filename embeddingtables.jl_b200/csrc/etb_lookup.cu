@@ -70,10 +70,16 @@ __device__ __forceinline__ void vec_add(Vec<T, VB>& acc, const Vec<T, VB>& v) {
 }
 
 // ------------------------------------------------------------------------------------ K2/K3
-template <typename T, int VB, int VPL, typename IdxT>
-__global__ void __launch_bounds__(kThreads)
+// Occupancy over per-warp depth (measured, profiles/README.md): with 4 rows in flight per lane the VPL = 1
+// kernel needs 32 registers -> 64 warps/SM; uniform C2 is at the DRAM limit either way (0.98 ms), the
+// L2-bound Zipf case gains 17 % (0.48 -> 0.40 ms) over 8 rows in flight at 54 registers.  Rows narrower
+// than 512 bytes keep 8 in flight (dim 16/32 lose 10-20 % with 4).
+// DEEP = false (rows of >= 512 bytes, G = 32): 4 rows in flight per lane, 32 registers, 64 warps/SM.
+// DEEP = true (narrower rows, several columns per warp): 8 rows in flight -- small rows need more of them.
+template <typename T, int VB, int VPL, typename IdxT, bool DEEP>
+__global__ void __launch_bounds__(kThreads, (VPL == 1 && !DEEP) ? (sizeof(T) == 4 ? 8 : 5) : (VPL <= 2 ? 4 : 3))
 pooled_kernel(const __grid_constant__ LookupParams P) {
-    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;  // row loads in flight per lane batch
+    constexpr int U = (VPL == 1 && !DEEP) ? 4 : ((8 / VPL) > 1 ? (8 / VPL) : 1);  // row loads in flight per lane batch
     using V = Vec<T, VB>;
     const LookupDesc& d = P.item[blockIdx.y];
     const int G = P.G;
@@ -271,9 +277,12 @@ static LookupClass classify(const etb_lookup_item& it) {
 template <typename T, int VB, typename IdxT>
 static cudaError_t launch_pooled_vpl(int vpl, dim3 grid, cudaStream_t s, const LookupParams& P) {
     switch (vpl) {
-        case 1: pooled_kernel<T, VB, 1, IdxT><<<grid, kThreads, 0, s>>>(P); break;
-        case 2: pooled_kernel<T, VB, 2, IdxT><<<grid, kThreads, 0, s>>>(P); break;
-        default: pooled_kernel<T, VB, 4, IdxT><<<grid, kThreads, 0, s>>>(P); break;
+        case 1:
+            if (P.G == 32) pooled_kernel<T, VB, 1, IdxT, false><<<grid, kThreads, 0, s>>>(P);
+            else pooled_kernel<T, VB, 1, IdxT, true><<<grid, kThreads, 0, s>>>(P);
+            break;
+        case 2: pooled_kernel<T, VB, 2, IdxT, true><<<grid, kThreads, 0, s>>>(P); break;
+        default: pooled_kernel<T, VB, 4, IdxT, true><<<grid, kThreads, 0, s>>>(P); break;
     }
     return cudaGetLastError();
 }
