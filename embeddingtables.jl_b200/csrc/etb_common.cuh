@@ -180,12 +180,6 @@ __device__ __forceinline__ void st_plain(char* p, const void* in) {
     }
 }
 
-// Start moving `bytes` (multiple of 16, 16-byte aligned address) from DRAM into L2 without occupying
-// registers or shared memory: one instruction per embedding row (sm_90+ bulk prefetch, SASS UBLKPF).
-__device__ __forceinline__ void prefetch_row_l2(const char* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 template <typename IdxT>
 __device__ __forceinline__ int64_t ld_index(const void* idx, int64_t pos) {
     return (int64_t)__ldg((const IdxT*)idx + pos);

@@ -29,30 +29,16 @@
 namespace etb {
 
 constexpr int kUThreads = 256;
-#ifndef ETB_UPDATE_UB
-#define ETB_UPDATE_UB 8
-#endif
-#ifndef ETB_UPDATE_U
-#define ETB_UPDATE_U 1
-#endif
-#ifndef ETB_UPDATE_PREFETCH
-#define ETB_UPDATE_PREFETCH 1
-#endif
-#ifndef ETB_UPDATE_EXACT_MIN_BLOCKS
-#define ETB_UPDATE_EXACT_MIN_BLOCKS 4
-#endif
-#ifndef ETB_UPDATE_EXACT_UB
-#define ETB_UPDATE_EXACT_UB 4
-#endif
-#ifndef ETB_UPDATE_USE_EXACT
-#define ETB_UPDATE_USE_EXACT 1
-#endif
-#ifndef ETB_UPDATE_RPL
-#define ETB_UPDATE_RPL 1
-#endif
-#ifndef ETB_UPDATE_MIN_BLOCKS
+// Tuning constants, all measured on C2 / B200 (profiles/README.md).  What matters for this access pattern is
+// occupancy and the absence of register spills (a spill of freshly loaded rows serialises the loads);
+// more bytes in flight per warp, bigger tiles and L2 bulk prefetch of the tile's rows did nothing.
+#define ETB_UPDATE_UB 8               /* generic kernel: buckets in flight per group (124 registers, 2 CTAs/SM) */
+#define ETB_UPDATE_U 1                /* generic kernel: extra member rows in flight in the short-duplicates loop */
+#define ETB_UPDATE_RPL 1              /* generic kernel: bucket records per lane (tile = 32 * RPL buckets; 2 gains 1.5 %) */
 #define ETB_UPDATE_MIN_BLOCKS 2
-#endif
+#define ETB_UPDATE_EXACT_UB 4         /* exact-fit kernel: buckets in flight per group (64 registers, 4 CTAs/SM) */
+#define ETB_UPDATE_EXACT_MIN_BLOCKS 4
+#define ETB_UPDATE_USE_EXACT 1
 constexpr int kUMaxItems = 96;
 
 // ------------------------------------------------------------------------------------ layout
@@ -481,12 +467,6 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         TileMeta m;
         m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
         m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
-        if (ETB_UPDATE_PREFETCH && VB == 16 && cnt > 0) {
-            // the whole tile's rows start streaming DRAM -> L2 now; the register loads below then
-            // find them in L2 (in-flight bytes no longer limited by registers)
-            prefetch_row_l2(m.row, (uint32_t)nvec * VB);
-            prefetch_row_l2(m.d0, (uint32_t)nvec * VB);
-        }
         s_meta[wbase + r * 32 + lane] = m;
         s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0, (int32_t)md.table.pad};
     }

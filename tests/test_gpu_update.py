@@ -324,3 +324,38 @@ def test_mixed_static_dynamic_ensemble(E, O):
         O.update(other, d, I[:, :, k], 0.7)
         differ += int(not np.array_equal(other.data, ref.data))
     assert differ > 0   # the two epilogues really round differently, so the test can tell them apart
+
+
+def test_cuda_graph_replay_of_a_step(E, O):
+    # the whole step (fused lookup + index! + update!) captured once and replayed: same result as eager
+    rng = np.random.default_rng(41)
+    base = [rng.standard_normal((64, 300)).astype(np.float32) for _ in range(3)]
+    I = E.as_device_indices(rng.integers(1, 301, (4, 128, 3)))
+    Ih = I.numpy()
+    delta = E.DeviceArray.from_numpy(rng.standard_normal((3 * 64, 128)).astype(np.float32))
+    tables = [E.SimpleEmbedding(b.copy(), E.Static(64)) for b in base]
+    out = E.DeviceArray.zeros((3 * 64, 128))
+    ix, opt = E.Indexer(), E.Descent(0.25)
+    grads = [E.SparseEmbeddingUpdate(E.Static(64), delta.rows(64 * k, 64 * k + 64), i) for k, i in enumerate(E.colwrap(I))]
+
+    def step():
+        E.maplookup_(E.PreallocationStrategy(), out, tables, I)
+        E.update_(opt, tables, grads, [ix])
+
+    replay = E.capture(step, warmup=1)      # 1 warm-up + 1 captured (not executed) = 1 update applied so far
+    replay()
+    replay()                                # 3 updates in total
+    refs = [O.Table(b.copy(order="F"), static=True) for b in base]
+    dh = delta.numpy()
+    for _ in range(3):
+        for k, r in enumerate(refs):
+            O.update(r, np.asfortranarray(dh[64 * k:64 * k + 64]), Ih[:, :, k], 0.25)
+    for t, r in zip(tables, refs):
+        assert np.array_equal(t.to_numpy(), r.data)
+    # the last replay's lookup saw the tables after 2 updates
+    refs2 = [O.Table(b.copy(order="F"), static=True) for b in base]
+    for _ in range(2):
+        for k, r in enumerate(refs2):
+            O.update(r, np.asfortranarray(dh[64 * k:64 * k + 64]), Ih[:, :, k], 0.25)
+    want = np.concatenate([O.lookup(r, Ih[:, :, k]) for k, r in enumerate(refs2)], axis=0)
+    assert np.array_equal(out.numpy(), want)
