@@ -230,11 +230,11 @@ def test_preallocation_prependrows_untouched(E, O):
 
 
 def test_maplookup_split_tables_many(E, O):
-    # more tables than one launch holds (kMaxItems = 96), split storage, ragged chunks
+    # more tables than one launch holds (kMaxItems = 256), split storage, ragged chunks
     rng = np.random.default_rng(4)
-    base = [rng.standard_normal((32, 64)).astype(np.float32) for _ in range(100)]
+    base = [rng.standard_normal((32, 64)).astype(np.float32) for _ in range(300)]
     tables = [E.SplitEmbedding(b, 24) for b in base]
-    inds = rng.integers(1, 65, (3, 40, 100))
+    inds = rng.integers(1, 65, (3, 40, 300))
     out = E.maplookup(E.PreallocationStrategy(), tables, inds).numpy()
     ref = np.concatenate([O.lookup(O.Table(b, cols_per_shard=24), inds[:, :, t]) for t, b in enumerate(base)], axis=0)
     assert np.array_equal(out, ref)

@@ -359,3 +359,45 @@ def test_cuda_graph_replay_of_a_step(E, O):
             O.update(r, np.asfortranarray(dh[64 * k:64 * k + 64]), Ih[:, :, k], 0.25)
     want = np.concatenate([O.lookup(r, Ih[:, :, k]) for k, r in enumerate(refs2)], axis=0)
     assert np.array_equal(out.numpy(), want)
+
+
+def test_many_table_ensemble_update(E, O):
+    # more tables than one update launch holds (kUMaxItems = 96): slots are chunked across launches
+    rng = np.random.default_rng(51)
+    nt = 130
+    base = [rng.standard_normal((16, 40)).astype(np.float32) for _ in range(nt)]
+    tables = [E.SimpleEmbedding(b.copy(), E.Static(16)) for b in base]
+    I = rng.integers(1, 41, (3, 50, nt))
+    deltas = [rng.standard_normal((16, 50)).astype(np.float32) for _ in range(nt)]
+    grads = [E.SparseEmbeddingUpdate(E.Static(16), d, I[:, :, k]) for k, d in enumerate(deltas)]
+    E.update_(E.Descent(0.2), tables, grads, [E.Indexer()])
+    for k, (t, b, d) in enumerate(zip(tables, base, deltas)):
+        ref = O.Table(b.copy(order="F"), static=True)
+        O.update(ref, d, I[:, :, k], 0.2)
+        assert np.array_equal(t.to_numpy(), ref.data), k
+
+
+def test_wide_keys_path(E, O):
+    # tables that DECLARE more than 2^32 (table, row) combinations use 64-bit sort keys; the indices only
+    # ever touch the first rows, so the declared size needs no memory
+    from embtab import _lib
+
+    class Huge(E.SimpleEmbedding):
+        def descriptor(self):
+            d = super().descriptor()
+            d.nrows = 1 << 33
+            return d
+
+    rng = np.random.default_rng(52)
+    base = [rng.standard_normal((32, 500)).astype(np.float32) for _ in range(3)]
+    tables = [Huge(b.copy(), E.Static(32)) for b in base]
+    I = rng.integers(1, 501, (4, 200, 3))
+    deltas = [rng.standard_normal((32, 200)).astype(np.float32) for _ in range(3)]
+    grads = [E.SparseEmbeddingUpdate(E.Static(32), d, I[:, :, k]) for k, d in enumerate(deltas)]
+    ix = E.Indexer()
+    E.update_(E.Descent(0.2), tables, grads, [ix])
+    assert ix.view.key_bytes == 8
+    for k, (t, b, d) in enumerate(zip(tables, base, deltas)):
+        ref = O.Table(b.copy(order="F"), static=True)
+        O.update(ref, d, I[:, :, k], 0.2)
+        assert np.array_equal(t.to_numpy(), ref.data)
