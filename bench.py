@@ -418,7 +418,7 @@ def run_sharded(args, rank, world, local):
         n += 1
         if events: events[2].record()
         ens.update_(opt, grads)
-        n += lib.etb_last_launch_count() + 9   # update kernels + the index! launches (etb_index counted 9)
+        n += lib.etb_last_launch_count() + ens.index_launches   # update kernels + the prefetched index! launches
         if events: events[3].record()
         launches[0] = n
 

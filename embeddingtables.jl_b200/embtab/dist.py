@@ -31,6 +31,7 @@ from . import _lib
 from .darray import DeviceArray, as_device_indices, current_stream_ptr
 from .lookup import _item, _run
 from .sparseupdate import Indexer, SparseEmbeddingUpdate, update_
+from .sparseupdate import prefetch_index as _prefetch_index
 from .tables import featuresize
 
 
@@ -131,6 +132,7 @@ class ShardedEnsemble:
         self._rows = (C.c_int64 * p.world)(*p.rows)
         self._row_off = (C.c_int64 * p.world)(*p.row_off)
         self.launches = 0
+        self.index_launches = 0
         if self.fused:
             self._setup_peer_memory()
 
@@ -250,11 +252,14 @@ class ShardedEnsemble:
         per = bag * p.batch_global
         return [DeviceArray(glob, shape, t * per, None, np_dtype) for t in range(t_mine)]
 
-    def forward(self, I, out: DeviceArray = None) -> DeviceArray:
+    def forward(self, I, out: DeviceArray = None, prefetch_index: bool = True) -> DeviceArray:
         p = self.plan
         Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else
                                              [I.lastdim(t) for t in range(I.shape[-1])])]
         self._I = Is
+        if prefetch_index:   # index! needs only the indices: run it beside the lookup and the exchange
+            _prefetch_index(self.indexer, self.tables, Is)
+            self.index_launches = _lib.lib().etb_last_launch_count()
         if self.fused:
             assert out is None, "fused mode writes into the peer-mapped self.out"
             return self._forward_fused(Is)
