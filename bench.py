@@ -74,7 +74,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -293,13 +293,14 @@ def run_ours(args):
     K = args.steps
     # ---- the timed region: K steps, index! overlapped with the forward unless --no-overlap
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        sync()
-        start.record()
-        for k in range(K):
-            step(overlap=overlap)
-        end.record()
-        sync()
+    clocks = ClockSampler(local)          # samples every 20 ms until the e2e region below has finished
+    clocks.__enter__()
+    sync()
+    start.record()
+    for k in range(K):
+        step(overlap=overlap)
+    end.record()
+    sync()
     ms_per_step = start.elapsed_time(end) / K
     # ---- per-kernel times: the same step with the phases back to back (CUDA events on the stream)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
@@ -326,6 +327,7 @@ def run_ours(args):
     sync()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / K
     e2e_ms = max(e0.elapsed_time(e1) / K, e2e_wall_ms)  # host-side work counts too
+    clocks.__exit__(None, None, None)
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = measured_peak_gbs()

@@ -19,7 +19,12 @@
 // members in order (one lane per feature vector, like the lookup kernels, so the sum has the
 // reference's association, src/sparseupdate.jl:114-120); then one read-modify-write of the
 // table row with a fused multiply-add (muladd, src/sparseupdate.jl:123-127) or two roundings
-// (:88).  One bucket = one row = one writer: no atomics anywhere.
+// (:88) -- a per-table choice, like the reference's dispatch.  One bucket = one row = one writer:
+// no atomics touch table data.  Kernels: sgd_update_exact_kernel / sgd_update_kernel (a warp per
+// tile of 32 buckets; buckets of up to 4 members finish here), bucket_tasks_kernel (buckets of 5..128
+// members and the 128-member chunks of longer ones), long_combine_kernel (chunk partials of a long
+// bucket, added in a fixed order).  The only atomics are worklist cursors; nothing that reaches a
+// result depends on their order.
 #include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 #include <vector>

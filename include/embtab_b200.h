@@ -219,8 +219,9 @@ int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item
 
 /* ---------------------------------------------------------------- update! ------------- */
 /* K5. For every bucket (distinct row k of table t): acc = 0; acc += delta_t[:, col] for the
- * bucket's members in order; A_t[:, k] = fma(-eta, acc, A_t[:, k]) (ETB_UPDATE_FMA) or
- * A_t[:, k] - eta*acc.  No atomics: one bucket = one table row = one writer.
+ * bucket's members in order; A_t[:, k] = fma(-eta, acc, A_t[:, k]) (ETB_UPDATE_FMA, in the call's
+ * flags for every table or in etb_update_item.flags per table) or A_t[:, k] - eta*acc.
+ * No atomics on table data: one bucket = one table row = one writer.
  * Replaces update!(table, update, indexer, alpha) reference src/sparseupdate.jl:57-154 and the
  * ensemble form :199-238.  `view_host` must be the result of etb_index on the SAME items.
  * eta is converted to the table's element type (reference src/sparseupdate.jl:173). */
