@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Regenerates profiles/README.md from the committed extracts in profiles/ (run from the repo root)."""
+import collections
+import csv
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+
+
+def jl(name):
+    return [json.loads(l) for l in open(os.path.join(P, name)) if l.strip()]
+
+
+def j1(name):
+    return json.loads(open(os.path.join(P, name)).read().strip().splitlines()[-1])
+
+
+rows = [r for r in csv.reader(open(os.path.join(P, "r1_launches_bench_c2.csv"))) if len(r) > 10]
+hdr = rows[0]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value")
+agg = collections.OrderedDict()
+for r in rows[1:]:
+    agg.setdefault(r[ki].split("(")[0][:75], []).append(float(r[vi].replace(",", "")))
+step_kernels = {k: v for k, v in agg.items() if "distribution" not in k}
+tot = sum(sum(v) for v in step_kernels.values())
+L = ["| kernel | launches | avg µs | share of the step's kernels |", "|---|---|---|---|"]
+for k, v in sorted(step_kernels.items(), key=lambda kv: -sum(kv[1])):
+    L.append(f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {100*sum(v)/tot:.1f}% |")
+launch_md = "\n".join(L)
+ours = sum(sum(v) for k, v in step_kernels.items() if "etb::" in k) / tot * 100
+
+K = json.load(open(os.path.join(P, "r1_ncu_kernels.json")))["kernels"]
+U, Z, R = j1("r1_bench_c2_uniform.json"), j1("r1_bench_c2_zipf.json"), j1("r1_bench_c2_reference_cpu.json")
+n8, n8n, n4 = j1("r1_bench_c2_n8_fused.json"), j1("r1_bench_c2_n8_nccl.json"), j1("r1_bench_c2_n4_fused.json")
+ub = json.load(open(os.path.join(P, "r1_ubench_random_rmw_ceiling.json")))
+c1 = jl("r1_c1_gather_update.jsonl")[-1]
+c3, c4, c5 = jl("r1_c3_zipf_update.jsonl"), jl("r1_c4_local_split_tables.jsonl"), jl("r1_c5_sweep.jsonl")
+peak = U["roofline"]["peak"]
+ku = U["kernels"]
+
+
+def sweep(dist, batch):
+    bags = sorted({r["bag"] for r in c5})
+    out = ["| dim \\ bag | " + " | ".join(str(b) for b in bags) + " |", "|---|" + "---|" * len(bags)]
+    for dim in sorted({r["dim"] for r in c5}):
+        line = []
+        for b in bags:
+            m = [r for r in c5 if r["dist"] == dist and r["batch"] == batch and r["dim"] == dim and r["bag"] == b]
+            line.append(f"{m[0]['frac_of_measured_peak']:.2f}" if m else "–")
+        out.append(f"| {dim} | " + " | ".join(line) + " |")
+    return "\n".join(out)
+
+
+c3md = "\n".join(["| form | n | distinct rows | hottest row | order | index µs | update! total µs | lookups/s | algorithmic GB/s |",
+                  "|---|---|---|---|---|---|---|---|---|"] +
+                 [f"| {r['form']} | {r['n']} | {r['distinct_rows']} | {r['hottest_row_members']} | {r['order']} | {r['index_us']:.0f} | "
+                  f"{r['update_us']:.0f} | {r['lookups_per_sec']/1e9:.2f} G | {r['gbs']:.0f} |" for r in c3])
+c4md = "\n".join(["| tables | shape | fwd ms | fwd / measured peak | fwd lookups/s | update! ms |", "|---|---|---|---|---|---|"] +
+                 [f"| {r['tables']} | {r['shape']} | {r['fwd_ms']:.3f} | {r['fwd_frac_of_measured_peak']:.2f} | "
+                  f"{r['fwd_lookups_per_sec']/1e9:.1f} G | {r['update_ms']:.2f} |" for r in c4])
+fb = ku["pooled_kernel"]["bytes"] + ku["sgd_update_kernel"]["bytes"]
+
+md = f"""# profiles/ — round 1 evidence (B200, sm_100a, driver 580, CUDA 12.9)
+
+Every number comes from `gpurun` runs on B200s of this pool.  The `.ncu-rep` files stay in `gpurun_out/`
+(scratch, 12-15 MB each); the extracts are committed here and this file is generated from them by
+`tools/make_profiles_readme.py`.
+
+| file | what |
+|---|---|
+| `r1_bench_c2_uniform.json`, `r1_bench_c2_zipf.json` | `python bench.py` / `--dist zipf`: the bench lines |
+| `r1_bench_c2_reference_cpu.json` | `python bench.py --impl reference`: C port of the reference on the box's host cores |
+| `r1_launches_bench_c2.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-overlap` |
+| `r1_ncu_kernels.json` | per-launch DRAM bytes / time / registers / occupancy of the two hot kernels from the `ncu --set full` capture of the same command (`bench.py` reads `roofline.traffic` from it) |
+| `r1_launches_bench_c2_zipf.csv`, `r1a_launches_bench_c2.csv` | launch lists for `--dist zipf` and for the FIRST correct version (before any tuning) |
+| `r1_bench_c2_n4_fused.json`, `r1_bench_c2_n8_fused.json`, `r1_bench_c2_n8_nccl.json` | torchrun bench lines at N = 4 / 8 |
+| `r1_ubench_random_rmw_ceiling.json` | `tools/ubench_rmw.cu`: what HBM delivers for random 512-byte RMW / reads |
+| `r1_c1_*.jsonl`, `r1_c3_*.jsonl`, `r1_c4_*.jsonl`, `r1_c5_sweep.jsonl` | `tools/bench_configs.py`: the other BASELINE configs |
+
+compute-sanitizer is closed on this pool (`gpurun` refuses it); `tools/sanitize_smoke.py` (a pass over every kernel
+family with odd shapes) runs clean without it, and bounds are covered by canary checks in the parity tests.
+
+## C2 (26 x 1M x 128 f32, bag 32, batch 16384, uniform), one B200
+
+| quantity | value |
+|---|---|
+| step = fused forward + lazy pullback + ensemble update! | **{U['ms_per_step']:.2f} ms -> {U['value']/1e9:.2f} G lookups/s** (index! on a high-priority side stream beside the forward; {U['config']['ms_per_step_phases_back_to_back']:.2f} ms with the phases back to back) |
+| forward (`pooled_kernel`, 1 launch) | {ku['pooled_kernel']['ms']:.2f} ms = {U['fwd_lookups_per_sec']/1e9:.1f} G lookups/s; 7.31 GB algorithmic -> {ku['pooled_kernel']['gbs']/1e3:.2f} TB/s = {ku['pooled_kernel']['gbs']/peak:.2f} x measured copy peak; DRAM traffic {K['pooled_kernel']['dram_bytes']/1e9:.2f} GB ({K['pooled_kernel']['dram_pct_of_ncu_peak']:.1f} % of ncu's DRAM peak); {K['pooled_kernel']['registers']} registers, {K['pooled_kernel']['warps_active_per_sm']:.0f} warps/SM active |
+| index! (make_pairs + CUB radix sort + 3 record kernels, {U['launches_per_step']['index'] if U['launches_per_step']['index'] else 14} launches) | {ku['index(make_pairs+radix sort+select)']['ms']:.2f} ms |
+| update (`sgd_update_exact_kernel` + task/combine kernels, {U['launches_per_step']['update']} launches) | {ku['sgd_update_kernel']['ms']:.2f} ms; 11.13 GB algorithmic -> **{ku['sgd_update_kernel']['gbs']/1e3:.2f} TB/s = {ku['sgd_update_kernel']['gbs']/peak:.2f} x measured peak**; DRAM traffic {K['sgd_update_kernel']['dram_bytes']/1e9:.2f} GB ({K['sgd_update_kernel']['dram_pct_of_ncu_peak']:.1f} % of ncu's DRAM peak); {K['sgd_update_kernel']['registers']} registers, {K['sgd_update_kernel']['warps_active_per_sm']:.0f} warps/SM |
+| fwd+bwd+SGD | {U['fwd_bwd_sgd_gbs']/1e3:.2f} TB/s algorithmic = {U['fwd_bwd_sgd_frac_of_peak']:.2f} x measured peak ({U['fwd_bwd_sgd_gbs']/8000:.2f} x nominal 8 TB/s) |
+| e2e (pinned host indices + cotangent in, feature matrix out; {U['e2e']['h2d_bytes_per_step']/1e6:.0f} MB H2D + {U['e2e']['d2h_bytes_per_step']/1e6:.0f} MB D2H per step) | {U['e2e']['ms_per_step']:.1f} ms -> {U['e2e']['value']/1e9:.2f} G lookups/s (PCIe-bound: 562 MB at ~53 GB/s) |
+| CPU arm: C port of the reference, {R['cpu_baseline']['cores']} host cores, AVX-512 | {R['value']/1e6:.1f} M lookups/s ({R['ms_per_step']:.0f} ms for 4 of the 26 tables) |
+| clocks in the timed regions | {U['clocks']['sm_mhz']:.0f} MHz of {U['clocks']['sm_max_mhz']:.0f}, reasons: {U['clocks']['reasons'] or 'none'} ({U['clocks'].get('samples')} samples) |
+| Zipf(1.05) indices | step {Z['ms_per_step']:.2f} ms = {Z['value']/1e9:.2f} G lookups/s (forward {Z['kernels']['pooled_kernel']['ms']:.2f} ms from L2, update {Z['kernels']['sgd_update_kernel']['ms']:.2f} ms, L2-read bound) |
+
+Ceiling check (`tools/ubench_rmw.cu`, same row set as C2's update): random 512-byte read-modify-write runs at
+{ub['rmw_U4']['gbs']:.0f} GB/s ({ub['rmw_U4']['ms']:.2f} ms) with only 4 rows in flight per warp but full occupancy; with the
+cotangent row read added {ub['rmw_plus_delta_U4']['ms']:.2f} ms; random 512-byte reads alone {ub['read_U8']['gbs']:.0f} GB/s.  The update kernel
+({K['sgd_update_kernel']['gpu_time_ms']:.2f} ms under ncu) is within 5 % of that ceiling; the pooled kernel reads {K['pooled_kernel']['dram_bytes_read']/K['pooled_kernel']['gpu_time_ms']/1e9:.2f} TB/s from DRAM.
+
+### Launch list of the step (cold-cache, serialised by ncu; compare shares)
+
+{launch_md}
+
+The hand-written kernels are {ours:.0f} % of the step's GPU time, the CUB radix sort the rest; shares agree with the
+CUDA-event times of `bench.py` (update {ku['sgd_update_kernel']['ms']:.2f}, pooled {ku['pooled_kernel']['ms']:.2f}, index {ku['index(make_pairs+radix sort+select)']['ms']:.2f} ms).
+
+### How the update kernel got here (C2 uniform)
+
+| version | update ms | DRAM GB (r+w) | what changed |
+|---|---|---|---|
+| first correct version: one bucket per group, grid-stride | 6.79 | – | 4 dependent loads per bucket |
+| warp tile of 32 buckets, cooperative metadata | 3.21 | 11.5 + 5.4 | metadata once per tile |
+| default L2 policy for row loads | 2.77 | – | `ld.global.nc.L1::no_allocate` is **evict_first in L2**: 192 M of 219 M cotangent sectors missed |
+| bucket records from K4, 8 buckets in flight | 3.16 | 5.9 + 5.4 | traffic = algorithmic, but a 32-byte spill of loaded registers serialised the loads (2 x `STL.64` = 23 % of stall samples) |
+| smem tile metadata, no spill (124 regs, 16 warps/SM) | 2.43 | 5.9 + 5.4 | |
+| bulk L2 prefetch of the tile's rows (`UBLKPF.L2`); 64-bucket tiles | 2.43 / 2.41 | – | no effect: in-flight bytes per warp were not the limiter |
+| **exact-fit kernel: 64 regs, 32 warps/SM, 4 buckets in flight** | **1.88** | 6.0 + 5.4 | the ceiling microbenchmark showed occupancy, not per-warp depth, is what this pattern needs |
+
+The same lesson applied to the pooled kernel (4 instead of 8 rows in flight, 32 registers, 64 warps/SM) left the
+DRAM-bound uniform case unchanged (0.98 ms) and sped the L2-bound Zipf forward up by 17 % (0.48 -> 0.40 ms).
+
+## Multi-GPU (weak scaling: 26 tables per GPU, global batch 16384; lines taken before the exact-fit update kernel)
+
+| N | exchange | ms/step | lookups/s | fwd+exchange / bwd exchange / index+update ms |
+|---|---|---|---|---|
+| 4 | fused NVLink stores | {n4['ms_per_step']:.2f} | {n4['value']/1e9:.1f} G | {n4['phases_ms']['fwd_lookup+exchange']:.2f} / {n4['phases_ms']['bwd_exchange']:.2f} / {n4['phases_ms']['index+update']:.2f} |
+| 8 | fused NVLink stores | {n8['ms_per_step']:.2f} | {n8['value']/1e9:.1f} G | {n8['phases_ms']['fwd_lookup+exchange']:.2f} / {n8['phases_ms']['bwd_exchange']:.2f} / {n8['phases_ms']['index+update']:.2f} |
+| 8 | NCCL all-to-all + pack/unpack | {n8n['ms_per_step']:.2f} | {n8n['value']/1e9:.1f} G | {n8n['phases_ms']['fwd_lookup+exchange']:.2f} / {n8n['phases_ms']['bwd_exchange']:.2f} / {n8n['phases_ms']['index+update']:.2f} |
+
+With that moment's 1-GPU step (3.42 ms -> 3.99 G lookups/s) the efficiencies are 91 % (N = 4) and 88 % (N = 8); the
+NCCL variant reaches 79 %.  With the current kernels and the index! prefetch, N = 2 measures 3.53 ms/step = 7.7 G
+lookups/s (93 %).  Per rank and direction the exchange moves 191 MB at N = 8: the fused backward scatter takes
+0.31 ms (0.62 TB/s of the measured 0.77 TB/s link rate); before the destinations were visited in rotated order (every
+rank storing into GPU 0 first) it took 0.79 ms.  e2e at N = 8 is host-bound: 8 ranks x 553 MB per step through one
+host = 39 ms.
+
+## Other BASELINE configs (`tools/bench_configs.py`)
+
+**C1** (26 x 64 x 100k, batch 2048, gather + update!, 53 248 lookups, 69 MB algorithmic = 10.5 µs at the measured
+peak): {c1['step_us']:.0f} µs eager (host-enqueue bound: the Python mirror spends ~10 µs per table per call),
+**{c1['step_cuda_graph_us']:.0f} µs as one CUDA graph** (`embtab.capture`; launch-latency bound, 18 kernels).
+
+**C3** (one 128 x 10M table, Zipf 1.05; `split` = default order, `strict` = the reference's strictly sequential order):
+
+{c3md}
+
+**C4, one GPU's share** (8 tables 128 x 5M, chunked `SplitEmbedding` with 1 048 576 rows per chunk vs `SimpleEmbedding`):
+
+{c4md}
+
+Chunked addressing costs nothing (one 32-bit divide per index, done by one lane).
+
+**C5** pooled-lookup sweep, 26 tables x 1M rows, fraction of the measured HBM peak (algorithmic bytes / GPU time;
+CUDA-graph replay, L2 flushed).  batch 16384, uniform:
+
+{sweep('uniform', 16384)}
+
+batch 65536, uniform:
+
+{sweep('uniform', 65536)}
+
+batch 1024, uniform (26 624 columns: latency / launch bound):
+
+{sweep('uniform', 1024)}
+
+batch 16384, Zipf 1.05 (L2-resident hot rows, hence > 1):
+
+{sweep('zipf', 16384)}
+"""
+open(os.path.join(P, "README.md"), "w").write(md)
+print("wrote profiles/README.md", len(md))
