@@ -6,10 +6,9 @@
 //
 // K4.  Every occurrence p of item t becomes the pair
 //          key = t << row_bits | (index - 1),      value = delta column of p (= p / bag)
-// All items are sorted at once by a stable LSD radix sort restricted to the bits the keys
-// actually use (cub::DeviceRadixSort -- library code, like cuBLAS would be for a GEMM), so
-// members of a bucket stay in occurrence order = the order remap! records (src/utils.jl:
-// 481-511).  Bucket starts are the positions whose key differs from the previous one,
+// All items are sorted at once by a hand-written stable LSD radix sort restricted to the bits the
+// keys actually use (etb_sort.cuh), so members of a bucket stay in occurrence order = the order
+// remap! records (src/utils.jl:481-511).  Bucket starts are the positions whose key differs from the previous one,
 // compacted into one 16-byte record per bucket by three small hand-written kernels (count heads per
 // tile, scan the tile counts, write records).  Buckets come out in ascending (table, row) order instead
 // of the reference's first-seen order; buckets are disjoint table rows, so results do not
@@ -26,10 +25,10 @@
 // bucket, added in a fixed order).  The only atomics are worklist cursors; nothing that reaches a
 // result depends on their order.
 #include <algorithm>
-#include <cub/device/device_radix_sort.cuh>
 #include <vector>
 
 #include "etb_common.cuh"
+#include "etb_sort.cuh"
 
 namespace etb {
 
@@ -258,18 +257,8 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
     L.off_long = off; off = align_up(off + L.max_long * sizeof(LongRec));
     L.off_chunks = off; off = align_up(off + L.max_tasks * sizeof(ChunkRec));
     L.off_partials = off; off = align_up(off + L.max_chunks * L.partial_pitch);
-    // CUB temp storage of the radix sort
-    size_t t_sort = 0;
-    const int end_bit = L.row_bits + L.slot_bits;
-    if (L.key_bytes == 4) {
-        cub::DoubleBuffer<uint32_t> k(nullptr, nullptr);
-        cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
-        ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
-    } else {
-        cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
-        cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
-        ETB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, k, v, (int64_t)n, 0, end_bit));
-    }
+    // scratch of the radix sort (tile histograms)
+    const size_t t_sort = rs_scratch_bytes((int64_t)n);
     L.off_temp = off;
     L.temp_bytes = t_sort;
     L.total = align_up(off + L.temp_bytes);
@@ -905,56 +894,20 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
             }
             ETB_LAUNCHED();
         }
-        // K4b: stable radix sort over the used key bits, then one record per bucket head.
-        // The pairs of one table are contiguous and tables are in slot order, so the ensemble can be
-        // sorted as 2^r groups of consecutive slots on the low (row_bits + slot_bits - r) bits only --
-        // the keys keep their full slot; inside a group the dropped top bits are constant.  When that
-        // saves a whole 8-bit radix pass over all the data (C2: 25 bits -> 24: 4 passes -> 3) it is
-        // worth the few extra launches.
-        int drop = 0;
-        if (L.n_total >= (1 << 20)) {
-            for (int r = 1; r <= std::min(L.slot_bits, 3); ++r)
-                if ((end_bit - r + 7) / 8 < (end_bit + 7) / 8) { drop = r; break; }
+        // K4b: stable radix sort over the used key bits (hand-written, etb_sort.cuh: 9/8/8-bit digits for C2's
+        // 25-bit keys = 3 passes), then one record per bucket head
+        int which = 0;
+        void* keys_out;
+        int32_t* vals_out;
+        if (L.key_bytes == 4) {
+            uint32_t* kb[2] = {(uint32_t*)keys[0], (uint32_t*)keys[1]};
+            if (int32_t st = radix_sort_pairs<uint32_t>(kb, vals, L.n_total, end_bit, (uint32_t*)(base + L.off_temp), stream, &which)) return st;
+        } else {
+            uint64_t* kb[2] = {(uint64_t*)keys[0], (uint64_t*)keys[1]};
+            if (int32_t st = radix_sort_pairs<uint64_t>(kb, vals, L.n_total, end_bit, (uint32_t*)(base + L.off_temp), stream, &which)) return st;
         }
-        const int sort_bits = end_bit - drop;
-        const int slots_per_group = 1 << (L.slot_bits - drop);
-        std::vector<int64_t> group_start;  // pair offset of each group (+ end)
-        {
-            int64_t off = 0;
-            for (int i = 0; i < n_items; ++i) {
-                if (i % slots_per_group == 0) group_start.push_back(off);
-                off += items[i].batch * (items[i].bag ? items[i].bag : 1);
-            }
-            group_start.push_back(off);
-        }
-        void* temp = base + L.off_temp;
-        void* keys_out = nullptr;
-        int32_t* vals_out = nullptr;
-        for (size_t g = 0; g + 1 < group_start.size(); ++g) {
-            const int64_t g0 = group_start[g], gn = group_start[g + 1] - g0;
-            if (gn == 0) continue;
-            size_t temp_bytes = L.temp_bytes;
-            cub::DoubleBuffer<int32_t> v(vals[0] + g0, vals[1] + g0);
-            void* kcur;
-            if (L.key_bytes == 4) {
-                cub::DoubleBuffer<uint32_t> k((uint32_t*)keys[0] + g0, (uint32_t*)keys[1] + g0);
-                ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, gn, 0, sort_bits, stream));
-                kcur = k.Current() - g0;
-            } else {
-                cub::DoubleBuffer<uint64_t> k((uint64_t*)keys[0] + g0, (uint64_t*)keys[1] + g0);
-                ETB_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, gn, 0, sort_bits, stream));
-                kcur = k.Current() - g0;
-            }
-            int32_t* vcur = v.Current() - g0;
-            if (!keys_out) { keys_out = kcur; vals_out = vcur; }
-            if (kcur != keys_out) {  // a group that ended in the other ping-pong buffer (different pass parity)
-                ETB_CUDA(cudaMemcpyAsync((char*)keys_out + g0 * L.key_bytes, (char*)kcur + g0 * L.key_bytes,
-                                         (size_t)gn * L.key_bytes, cudaMemcpyDeviceToDevice, stream));
-                ETB_CUDA(cudaMemcpyAsync(vals_out + g0, vcur + g0, (size_t)gn * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream));
-            }
-            // CUB radix sort launches: histogram + exclusive sum + one onesweep pass per 8 key bits
-            launch_counter() += 2 + (sort_bits + 7) / 8;
-        }
+        keys_out = keys[which];
+        vals_out = vals[which];
         keys[0] = keys_out;
         if (L.key_bytes == 4) {
             if (int32_t st = select_heads<uint32_t>(tiles, (const uint32_t*)keys[0], vals_out, recs, nnz, L.n_total, stream)) return st;
