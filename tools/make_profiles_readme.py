@@ -85,9 +85,9 @@ family with odd shapes) runs clean without it, and bounds are covered by canary 
 
 | quantity | value |
 |---|---|
-| step = fused forward + lazy pullback + ensemble update! | **{U['ms_per_step']:.2f} ms -> {U['value']/1e9:.2f} G lookups/s** (index! on a high-priority side stream beside the forward; {U['config']['ms_per_step_phases_back_to_back']:.2f} ms with the phases back to back) |
+| step = fused forward + lazy pullback + ensemble update! | **{U['ms_per_step']:.2f} ms -> {U['value']/1e9:.2f} G lookups/s** (index! on a side stream beside the forward; {U['config']['ms_per_step_phases_back_to_back']:.2f} ms with the phases back to back) |
 | forward (`pooled_kernel`, 1 launch) | {ku['pooled_kernel']['ms']:.2f} ms = {U['fwd_lookups_per_sec']/1e9:.1f} G lookups/s; 7.31 GB algorithmic -> {ku['pooled_kernel']['gbs']/1e3:.2f} TB/s = {ku['pooled_kernel']['gbs']/peak:.2f} x measured copy peak; DRAM traffic {K['pooled_kernel']['dram_bytes']/1e9:.2f} GB ({K['pooled_kernel']['dram_pct_of_ncu_peak']:.1f} % of ncu's DRAM peak); {K['pooled_kernel']['registers']} registers, {K['pooled_kernel']['warps_active_per_sm']:.0f} warps/SM active |
-| index! (make_pairs + CUB radix sort + 3 record kernels, {U['launches_per_step']['index'] if U['launches_per_step']['index'] else 14} launches) | {ku['index(make_pairs+radix sort+select)']['ms']:.2f} ms |
+| index! (make_pairs + hand-written radix sort (3 passes x 3 kernels) + 3 record kernels, 13 launches) | {ku['index(make_pairs+radix sort+select)']['ms']:.2f} ms |
 | update (`sgd_update_exact_kernel` + task/combine kernels, {U['launches_per_step']['update']} launches) | {ku['sgd_update_kernel']['ms']:.2f} ms; 11.13 GB algorithmic -> **{ku['sgd_update_kernel']['gbs']/1e3:.2f} TB/s = {ku['sgd_update_kernel']['gbs']/peak:.2f} x measured peak**; DRAM traffic {K['sgd_update_kernel']['dram_bytes']/1e9:.2f} GB ({K['sgd_update_kernel']['dram_pct_of_ncu_peak']:.1f} % of ncu's DRAM peak); {K['sgd_update_kernel']['registers']} registers, {K['sgd_update_kernel']['warps_active_per_sm']:.0f} warps/SM |
 | fwd+bwd+SGD | {U['fwd_bwd_sgd_gbs']/1e3:.2f} TB/s algorithmic = {U['fwd_bwd_sgd_frac_of_peak']:.2f} x measured peak ({U['fwd_bwd_sgd_gbs']/8000:.2f} x nominal 8 TB/s) |
 | e2e (pinned host indices + cotangent in, feature matrix out; {U['e2e']['h2d_bytes_per_step']/1e6:.0f} MB H2D + {U['e2e']['d2h_bytes_per_step']/1e6:.0f} MB D2H per step) | {U['e2e']['ms_per_step']:.1f} ms -> {U['e2e']['value']/1e9:.2f} G lookups/s (PCIe-bound: 562 MB at ~53 GB/s) |
@@ -104,7 +104,7 @@ cotangent row read added {ub['rmw_plus_delta_U4']['ms']:.2f} ms; random 512-byte
 
 {launch_md}
 
-The hand-written kernels are {ours:.0f} % of the step's GPU time, the CUB radix sort the rest; shares agree with the
+Every kernel of the step is hand-written ({ours:.0f} % of the GPU time in `etb::` kernels); shares agree with the
 CUDA-event times of `bench.py` (update {ku['sgd_update_kernel']['ms']:.2f}, pooled {ku['pooled_kernel']['ms']:.2f}, index {ku['index(make_pairs+radix sort+select)']['ms']:.2f} ms).
 
 ### How the update kernel got here (C2 uniform)
