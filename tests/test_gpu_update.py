@@ -401,3 +401,31 @@ def test_wide_keys_path(E, O):
         ref = O.Table(b.copy(order="F"), static=True)
         O.update(ref, d, I[:, :, k], 0.2)
         assert np.array_equal(t.to_numpy(), ref.data)
+
+
+@pytest.mark.parametrize("n,nrows,wide", [(1_000_003, 5000, False), (300_000, 70_000_000, False), (200_000, 9000, True), (77, 50, False)])
+def test_index_sort_is_a_stable_sort(E, n, nrows, wide):
+    # the hand-written radix sort behind index!: sorted by row, and STABLE -- members of a bucket keep the
+    # occurrence order (what remap! records, reference src/utils.jl:481-511); checked against numpy's stable sort
+    from embtab.sparseupdate import _IndicesOnly, _peek
+
+    class Declared(E.SimpleEmbedding):          # only the declared row count matters to index!
+        def descriptor(self):
+            d = super().descriptor()
+            d.nrows = (1 << 34) if wide else nrows
+            return d
+
+    rng = np.random.default_rng(n)
+    table = Declared(np.zeros((4, 8), np.float32))
+    I = rng.integers(1, nrows + 1, n)
+    ix = E.Indexer()
+    E.index_(ix, table, _IndicesOnly(table, I))   # index! needs the indices only
+    v = ix.view
+    keys = _peek(v.keys, n, np.uint32 if v.key_bytes == 4 else np.uint64).astype(np.int64)
+    mp = _peek(v.map, n, np.int32)
+    order = np.argsort(I, kind="stable")
+    assert v.key_bytes == (8 if wide else 4)
+    assert np.array_equal(keys, I[order] - 1)
+    assert np.array_equal(mp, order.astype(np.int32))
+    nnz = int(_peek(v.nnz, 1, np.int64)[0])
+    assert nnz == np.unique(I).size

@@ -104,7 +104,8 @@ cotangent row read added {ub['rmw_plus_delta_U4']['ms']:.2f} ms; random 512-byte
 
 {launch_md}
 
-Every kernel of the step is hand-written ({ours:.0f} % of the GPU time in `etb::` kernels); shares agree with the
+(The list also contains the e2e region's forwards, which run as 4 column chunks per step -- hence the lower
+pooled average.)  Every kernel of the step is hand-written ({ours:.0f} % of the GPU time in `etb::` kernels); shares agree with the
 CUDA-event times of `bench.py` (update {ku['sgd_update_kernel']['ms']:.2f}, pooled {ku['pooled_kernel']['ms']:.2f}, index {ku['index(make_pairs+radix sort+select)']['ms']:.2f} ms).
 
 ### How the update kernel got here (C2 uniform)
