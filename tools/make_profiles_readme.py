@@ -123,20 +123,20 @@ CUDA-event times of `bench.py` (update {ku['sgd_update_kernel']['ms']:.2f}, pool
 The same lesson applied to the pooled kernel (4 instead of 8 rows in flight, 32 registers, 64 warps/SM) left the
 DRAM-bound uniform case unchanged (0.98 ms) and sped the L2-bound Zipf forward up by 17 % (0.48 -> 0.40 ms).
 
-## Multi-GPU (weak scaling: 26 tables per GPU, global batch 16384; lines taken before the exact-fit update kernel)
+## Multi-GPU (weak scaling: 26 tables per GPU, global batch 16384)
 
-| N | exchange | ms/step | lookups/s | fwd+exchange / bwd exchange / index+update ms |
-|---|---|---|---|---|
-| 4 | fused NVLink stores | {n4['ms_per_step']:.2f} | {n4['value']/1e9:.1f} G | {n4['phases_ms']['fwd_lookup+exchange']:.2f} / {n4['phases_ms']['bwd_exchange']:.2f} / {n4['phases_ms']['index+update']:.2f} |
-| 8 | fused NVLink stores | {n8['ms_per_step']:.2f} | {n8['value']/1e9:.1f} G | {n8['phases_ms']['fwd_lookup+exchange']:.2f} / {n8['phases_ms']['bwd_exchange']:.2f} / {n8['phases_ms']['index+update']:.2f} |
-| 8 | NCCL all-to-all + pack/unpack | {n8n['ms_per_step']:.2f} | {n8n['value']/1e9:.1f} G | {n8n['phases_ms']['fwd_lookup+exchange']:.2f} / {n8n['phases_ms']['bwd_exchange']:.2f} / {n8n['phases_ms']['index+update']:.2f} |
+| N | exchange | code state | ms/step | lookups/s | fwd+exchange / bwd exchange / index+update ms |
+|---|---|---|---|---|---|
+| 8 | fused NVLink stores | current | {n8['ms_per_step']:.2f} | **{n8['value']/1e9:.1f} G** | {n8['phases_ms']['fwd_lookup+exchange']:.2f} / {n8['phases_ms']['bwd_exchange']:.2f} / {n8['phases_ms']['index+update']:.2f} |
+| 4 | fused NVLink stores | earlier (update kernel 2.45 ms, no index! prefetch) | {n4['ms_per_step']:.2f} | {n4['value']/1e9:.1f} G | {n4['phases_ms']['fwd_lookup+exchange']:.2f} / {n4['phases_ms']['bwd_exchange']:.2f} / {n4['phases_ms']['index+update']:.2f} |
+| 8 | NCCL all-to-all + pack/unpack | earlier (same state as the N = 4 line) | {n8n['ms_per_step']:.2f} | {n8n['value']/1e9:.1f} G | {n8n['phases_ms']['fwd_lookup+exchange']:.2f} / {n8n['phases_ms']['bwd_exchange']:.2f} / {n8n['phases_ms']['index+update']:.2f} |
 
-With that moment's 1-GPU step (3.42 ms -> 3.99 G lookups/s) the efficiencies are 91 % (N = 4) and 88 % (N = 8); the
-NCCL variant reaches 79 %.  With the current kernels and the index! prefetch, N = 2 measures 3.53 ms/step = 7.7 G
-lookups/s (93 %).  Per rank and direction the exchange moves 191 MB at N = 8: the fused backward scatter takes
-0.31 ms (0.62 TB/s of the measured 0.77 TB/s link rate); before the destinations were visited in rotated order (every
-rank storing into GPU 0 first) it took 0.79 ms.  e2e at N = 8 is host-bound: 8 ranks x 553 MB per step through one
-host = 39 ms.
+Current N = 8 vs 8 x the current 1-GPU step ({U['value']/1e9:.2f} G lookups/s): {n8['value']/8/U['value']*100:.0f} % weak-scaling efficiency.  In the earlier
+state (1-GPU 3.99 G lookups/s) the fused exchange reached 88 % at N = 8 (28.3 G) and 91 % at N = 4, the NCCL
+variant 79 %.  Per rank and direction the exchange moves 191 MB at N = 8; the fused backward scatter alone took
+0.31 ms (0.62 TB/s of the measured 0.77 TB/s link rate) -- 0.79 ms before the destinations were visited in
+rotated order (every rank storing into GPU 0 first).  e2e at N = 8 is host-bound: 8 ranks x 553 MB per step
+through one host = 39 ms.
 
 ## Other BASELINE configs (`tools/bench_configs.py`)
 
