@@ -246,3 +246,59 @@ def test_missing_library_fails_loudly(E, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libembtab_b200.so")
     with pytest.raises(E.EmbTabError):
         E.lookup(E.SimpleEmbedding(np.zeros((4, 4), np.float32)), [1])
+
+
+def test_direct_c_entry_points(E, O):
+    # the single-table C entry points a Julia `ccall` would use (the mirror itself goes through etb_maplookup):
+    # etb_gather, etb_pooled_sum, etb_index_and_update, runtime alloc/copy/stream
+    import ctypes as C
+
+    from embtab import _lib
+    lib = _lib.lib()
+    rng = np.random.default_rng(77)
+    dim, nrows, bag, batch = 64, 500, 6, 300
+    base = np.asfortranarray(rng.standard_normal((dim, nrows)).astype(np.float32))
+    I = np.asfortranarray(rng.integers(1, nrows + 1, (bag, batch)))
+    stream = C.c_void_p()
+    _lib.check(lib.etb_stream_create(C.byref(stream)))
+    ptrs = []
+
+    def dmalloc(nbytes):
+        p = C.c_void_p()
+        _lib.check(lib.etb_malloc(C.byref(p), nbytes))
+        ptrs.append(p)
+        return p
+
+    d_table, d_idx, d_out = dmalloc(base.nbytes), dmalloc(I.nbytes), dmalloc(dim * batch * 4)
+    _lib.check(lib.etb_memcpy_h2d(d_table, base.ctypes.data, base.nbytes, stream))
+    _lib.check(lib.etb_memcpy_h2d(d_idx, I.ctypes.data, I.nbytes, stream))
+    t = _lib.Table(d_table.value, None, nrows, 0, dim, dim, _lib.F32, 0)
+    out = np.empty((dim, batch), np.float32, order="F")
+    _lib.check(lib.etb_pooled_sum(d_out, dim, C.byref(t), d_idx, _lib.I64, bag, batch, bag, stream))
+    _lib.check(lib.etb_memcpy_d2h(out.ctypes.data, d_out, out.nbytes, stream))
+    _lib.check(lib.etb_stream_sync(stream))
+    assert np.array_equal(out, O.lookup(O.Table(base), I))
+    _lib.check(lib.etb_gather(d_out, dim, C.byref(t), d_idx, _lib.I64, batch, stream))   # first `batch` indices as a vector
+    _lib.check(lib.etb_memcpy_d2h(out.ctypes.data, d_out, out.nbytes, stream))
+    _lib.check(lib.etb_stream_sync(stream))
+    assert np.array_equal(out, O.lookup(O.Table(base), I.ravel(order="F")[:batch]))
+    # update!: etb_index_workspace_bytes + etb_index_and_update
+    delta = np.asfortranarray(rng.standard_normal((dim, batch)).astype(np.float32))
+    d_delta = dmalloc(delta.nbytes)
+    _lib.check(lib.etb_memcpy_h2d(d_delta, delta.ctypes.data, delta.nbytes, stream))
+    item = _lib.UpdateItem(t, d_delta.value, dim, d_idx.value, batch, bag, bag, _lib.I64, _lib.UPDATE_FMA)
+    need = C.c_size_t()
+    _lib.check(lib.etb_index_workspace_bytes(C.byref(item), 1, C.byref(need)))
+    ws = dmalloc(need.value)
+    assert lib.etb_index_and_update(ws, need.value - 1, C.byref(item), 1, 0.5, 0, stream) == 3   # ETB_ERR_WORKSPACE
+    assert b"workspace" in lib.etb_last_error()
+    _lib.check(lib.etb_index_and_update(ws, need.value, C.byref(item), 1, 0.5, 0, stream))
+    got = np.empty_like(base)
+    _lib.check(lib.etb_memcpy_d2h(got.ctypes.data, d_table, got.nbytes, stream))
+    _lib.check(lib.etb_stream_sync(stream))
+    ref = O.Table(base.copy(order="F"), static=True)
+    O.update(ref, delta, I, 0.5)
+    assert np.array_equal(got, ref.data)
+    for p in ptrs:
+        _lib.check(lib.etb_free(p))
+    _lib.check(lib.etb_stream_destroy(stream))
