@@ -56,6 +56,12 @@ __global__ void __launch_bounds__(kRsThreads) rs_hist_kernel(const KeyT* __restr
     for (int d = threadIdx.x; d < nb; d += kRsThreads) tile_hist[(size_t)d * ntiles + blockIdx.x] = cnt[d];
 }
 
+template <typename KeyT>
+struct alignas(sizeof(KeyT) == 4 ? 8 : 16) RsPair {
+    KeyT k;
+    int32_t v;
+};
+
 // exclusive scan of `v` over the block (256 threads); returns the exclusive prefix, total in *total
 __device__ __forceinline__ uint32_t rs_block_exscan(uint32_t v, uint32_t* warp_tot /* [8] smem */, uint32_t* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -105,9 +111,9 @@ __global__ void __launch_bounds__(kRsThreads, ETB_RS_MIN_BLOCKS) rs_scatter_kern
                                                                 int shift, int nb, const uint32_t* __restrict__ tile_hist,
                                                                 const uint32_t* __restrict__ digit_total, int ntiles) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
-    KeyT* skey = (KeyT*)rs_smem;                                           // [kRsTile]
-    int32_t* sval = (int32_t*)(skey + kRsTile);                            // [kRsTile]
-    uint16_t* wcount = (uint16_t*)(sval + kRsTile);                        // [kRsWarps][kRsMaxBins] counts, then warp prefixes
+    RsPair<KeyT>* spair = (RsPair<KeyT>*)rs_smem;                           // [kRsTile] (key, value) staged together:
+                                                                           // one shared-memory store / load per element
+    uint16_t* wcount = (uint16_t*)(spair + kRsTile);                       // [kRsWarps][kRsMaxBins] counts, then warp prefixes
     uint32_t* tstart = (uint32_t*)(wcount + kRsWarps * kRsMaxBins);        // [kRsMaxBins] tile-local start of each digit
     uint32_t* gbase = tstart + kRsMaxBins;                                 // [kRsMaxBins] global position of that start
     uint32_t* warp_tot = gbase + kRsMaxBins;                               // [kRsWarps]
@@ -195,24 +201,23 @@ __global__ void __launch_bounds__(kRsThreads, ETB_RS_MIN_BLOCKS) rs_scatter_kern
         const uint32_t d = dr[i] >> 16;
         if (d != 0xffffu) {
             const uint32_t q2 = tstart[d] + wcount[warp * kRsMaxBins + d] + (dr[i] & 0xffffu);
-            skey[q2] = k[i];
-            sval[q2] = v[i];
+            spair[q2] = RsPair<KeyT>{k[i], v[i]};
         }
     }
     __syncthreads();
     // write the digit runs out: consecutive threads, consecutive addresses inside a run
     for (int q = threadIdx.x; q < tile_n; q += kRsThreads) {
-        const KeyT key = skey[q];
-        const uint32_t d = (uint32_t)(key >> shift) & dmask;
+        const RsPair<KeyT> pr = spair[q];
+        const uint32_t d = (uint32_t)(pr.k >> shift) & dmask;
         const uint32_t g = gbase[d] + (uint32_t)q;  // modular uint32 arithmetic: gbase may have wrapped below zero
-        kout[g] = key;
-        vout[g] = sval[q];
+        kout[g] = pr.k;
+        vout[g] = pr.v;
     }
 }
 
 template <typename KeyT>
 constexpr size_t rs_scatter_smem() {
-    return (size_t)kRsTile * (sizeof(KeyT) + sizeof(int32_t)) + (size_t)kRsWarps * kRsMaxBins * sizeof(uint16_t) +
+    return (size_t)kRsTile * sizeof(RsPair<KeyT>) + (size_t)kRsWarps * kRsMaxBins * sizeof(uint16_t) +
            2 * kRsMaxBins * sizeof(uint32_t) + kRsWarps * sizeof(uint32_t);
 }
 
