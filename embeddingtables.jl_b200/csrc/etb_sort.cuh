@@ -131,10 +131,14 @@ __global__ void __launch_bounds__(kRsThreads, ETB_RS_MIN_BLOCKS) rs_scatter_kern
     uint32_t dr[kRsItems];  // digit << 16 | rank of the element among equal digits of its warp
     uint16_t* mycount = wcount + warp * kRsMaxBins;
 #pragma unroll
+    for (int i = 0; i < kRsItems; ++i) {  // all key loads first: the ranking loop's __syncwarp() would pin them in place
+        const int q = warp * (32 * kRsItems) + i * 32 + lane;
+        k[i] = q < tile_n ? __ldg(kin + tile_base + q) : (KeyT)0;
+    }
+#pragma unroll
     for (int i = 0; i < kRsItems; ++i) {
         const int q = warp * (32 * kRsItems) + i * 32 + lane;
         const bool valid = q < tile_n;
-        k[i] = valid ? __ldg(kin + tile_base + q) : (KeyT)0;
         const uint32_t d = valid ? ((uint32_t)(k[i] >> shift) & dmask) : 0xffffu;  // invalid lanes form their own group
         // lanes with my digit: one ballot per digit bit (__match_any_sync is several times slower on sm_100)
         unsigned peers = __ballot_sync(0xffffffffu, valid);
