@@ -518,8 +518,8 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
     }
 }
 
-// Exact-fit specialisation of the main kernel: VB = 16 and the row is exactly G*VPL vectors (every
-// power-of-two dim, e.g. dim 128 f32 -> G = 32, VPL = 1).  G, the vector offsets and the single pass
+// Single-pass specialisation of the main kernel: VB = 16 and the row fits G*VPL vectors (every dim that is
+// a multiple of 4 floats up to 512, e.g. dim 128 f32 -> G = 32, VPL = 1; dim 80 -> 20 of 32 lanes active).  G, the vector offsets and the single pass
 // are compile-time, the few-duplicates loop needs no shuffles (every lane reads the same map entry:
 // one broadcast transaction), so the kernel fits in few registers and runs at 3-4x the occupancy of
 // the generic one -- which is what the random 512-byte read-modify-write pattern wants: the HBM
@@ -534,6 +534,10 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
     __shared__ TileMeta2 s_meta2[kUThreads];
     const int lane = threadIdx.x & 31;
     const int voff = (lane & (G - 1)) * VB;                  // my first vector of a row
+    // rows narrower than G*VPL vectors (e.g. dim 80 = 20 vectors on G = 32): the surplus lanes idle
+    bool on[VPL];
+#pragma unroll
+    for (int p = 0; p < VPL; ++p) on[p] = (lane & (G - 1)) + p * G < P.nvec;
     const int gbase = threadIdx.x & ~(G - 1);                // my group's slice of the shared arrays
     const int64_t nnz = *P.nnz;
     int64_t s_begin = 0, s_end = nnz;
@@ -577,8 +581,10 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                 const TileMeta m = s_meta[gbase + k0 + u];
 #pragma unroll
                 for (int p = 0; p < VPL; ++p) {
-                    ld_plain<VB>(&old[u][p], m.row + voff + p * G * VB);
-                    ld_row<VB>(&acc[u][p], m.d0 + voff + p * G * VB);
+                    if (on[p]) {
+                        ld_plain<VB>(&old[u][p], m.row + voff + p * G * VB);
+                        ld_row<VB>(&acc[u][p], m.d0 + voff + p * G * VB);
+                    }
                 }
             }
         }
@@ -596,20 +602,24 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                         const char* r = d.delta + (int64_t)__ldg(P.map + m2.start + i) * d.ld_delta_bytes + voff;
 #pragma unroll
                         for (int p = 0; p < VPL; ++p) {
-                            V v;
-                            ld_row<VB>(&v, r + p * G * VB);
+                            if (on[p]) {
+                                V v;
+                                ld_row<VB>(&v, r + p * G * VB);
 #pragma unroll
-                            for (int e = 0; e < V::NE; ++e) acc[u][p].e[e] = acc[u][p].e[e] + v.e[e];
+                                for (int e = 0; e < V::NE; ++e) acc[u][p].e[e] = acc[u][p].e[e] + v.e[e];
+                            }
                         }
                     }
                 }
                 char* row = const_cast<char*>(s_meta[gbase + k0 + u].row) + voff;
 #pragma unroll
                 for (int p = 0; p < VPL; ++p) {
-                    V out;
+                    if (on[p]) {
+                        V out;
 #pragma unroll
-                    for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
-                    st_plain<VB>(row + p * G * VB, &out);
+                        for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
+                        st_plain<VB>(row + p * G * VB, &out);
+                    }
                 }
             }
         }
@@ -819,7 +829,7 @@ static void launch_update_vb(int which, const UpdClass& c, int grid, cudaStream_
 template <typename T>
 static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     constexpr int UB = ETB_UPDATE_EXACT_UB;
-    if (c.vb != 16 || c.nvec != c.G * c.vpl) return false;
+    if (c.vb != 16 || c.nvec > c.G * c.vpl) return false;  // 16-byte vectors, row fits one pass
 #define ETB_EXACT(VPLV, GV, UBV)                                                         \
     if (c.vpl == VPLV && c.G == GV) {                                                    \
         sgd_update_exact_kernel<T, VPLV, GV, (UBV)><<<grid, kUThreads, 0, s>>>(P);       \

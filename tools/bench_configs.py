@@ -221,11 +221,36 @@ def config_c4local(fh):
         torch.cuda.empty_cache()
 
 
+def config_update_sweep(fh):
+    """update!(Descent) over feature sizes: 26 tables x 1M rows, bag 32, batch 16384, uniform indices (C2's shape
+    with dim varied) -- checks that the update path has no cliffs away from dim 128."""
+    nrows, nt, bag, batch = 1_000_000, 26, 32, 16384
+    rng = np.random.default_rng(0xE7AB1E + 6)
+    I_host = rng.integers(1, nrows + 1, (bag, batch, nt))
+    u = sum(int(np.unique(I_host[:, :, t]).size) for t in range(nt))
+    I = E.DeviceArray.from_numpy(I_host)
+    Is = list(E.colwrap(I))
+    for dim in (16, 32, 64, 80, 128, 256, 512):
+        tables = rand_tables(nt, dim, nrows)
+        delta = E.DeviceArray(torch.randn(nt * dim * batch, device="cuda"), (nt * dim, batch))
+        grads = [E.SparseEmbeddingUpdate(E.Static(dim), delta.rows(k * dim, (k + 1) * dim), i) for k, i in enumerate(Is)]
+        indexer, opt = E.Indexer(), E.Descent(0.01)
+        E.index_(indexer, tables, grads)
+        t_k = timeit(lambda: E.sparseupdate._apply(tables, grads, indexer, 0.01), iters=10, warmup=3)
+        t_i = timeit(lambda: E.index_(indexer, tables, grads), iters=10, warmup=3)
+        b = nt * batch * dim * 4 + 2 * u * dim * 4 + nt * batch * bag * 4
+        emit({"config": "update-sweep", "dim": dim, "kernel_ms": t_k, "index_ms": t_i, "algorithmic_bytes": b,
+              "kernel_gbs": b / t_k / 1e6, "kernel_frac_of_measured_peak": b / t_k / 1e6 / PEAK,
+              "lookups_per_sec_update": nt * batch * bag / ((t_k + t_i) * 1e-3)}, fh)
+        del tables, delta, grads, indexer
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4local", "c5", "c5quick"])
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4local", "c5", "c5quick", "update"])
     ap.add_argument("--out")
     a = ap.parse_args()
     E._lib.check(E.lib().etb_init(0))
     fh = open(a.out, "a") if a.out else None
-    {"c1": config_c1, "c3": config_c3, "c4local": config_c4local, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)
+    {"c1": config_c1, "c3": config_c3, "c4local": config_c4local, "update": config_update_sweep, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)

@@ -36,6 +36,9 @@ n8, n8n, n4 = j1("r1_bench_c2_n8_fused.json"), j1("r1_bench_c2_n8_nccl.json"), j
 ub = json.load(open(os.path.join(P, "r1_ubench_random_rmw_ceiling.json")))
 c1 = jl("r1_c1_gather_update.jsonl")[-1]
 c3, c4, c5 = jl("r1_c3_zipf_update.jsonl"), jl("r1_c4_local_split_tables.jsonl"), jl("r1_c5_sweep.jsonl")
+usw = jl("r1_update_sweep.jsonl")
+uswmd = "\n".join(["| dim | update kernels ms | index! ms | kernels: algorithmic GB/s | / measured peak |", "|---|---|---|---|---|"] +
+                  [f"| {r['dim']} | {r['kernel_ms']:.2f} | {r['index_ms']:.2f} | {r['kernel_gbs']:.0f} | {r['kernel_frac_of_measured_peak']:.2f} |" for r in usw])
 peak = U["roofline"]["peak"]
 ku = U["kernels"]
 
@@ -153,6 +156,11 @@ peak): {c1['step_us']:.0f} µs eager (host-enqueue bound: the Python mirror spen
 {c4md}
 
 Chunked addressing costs nothing (one 32-bit divide per index, done by one lane).
+
+**update! over feature sizes** (C2's shape with dim varied: 26 tables x 1M rows, bag 32, batch 16384, uniform; dim 80
+is not a power of two -- 20 of a group's 32 lanes are active; dims 16-64 move 64-256-byte rows):
+
+{uswmd}
 
 **C5** pooled-lookup sweep, 26 tables x 1M rows, fraction of the measured HBM peak (algorithmic bytes / GPU time;
 CUDA-graph replay, L2 flushed).  batch 16384, uniform:
