@@ -33,6 +33,7 @@ ours = sum(sum(v) for k, v in step_kernels.items() if "etb::" in k) / tot * 100
 K = json.load(open(os.path.join(P, "r1_ncu_kernels.json")))["kernels"]
 U, Z, R = j1("r1_bench_c2_uniform.json"), j1("r1_bench_c2_zipf.json"), j1("r1_bench_c2_reference_cpu.json")
 n8, n8n, n4 = j1("r1_bench_c2_n8_fused.json"), j1("r1_bench_c2_n8_nccl.json"), j1("r1_bench_c2_n4_fused.json")
+n2 = j1("r1_bench_c2_n2_fused.json")
 ub = json.load(open(os.path.join(P, "r1_ubench_random_rmw_ceiling.json")))
 c1 = jl("r1_c1_gather_update.jsonl")[-1]
 c3, c4, c5 = jl("r1_c3_zipf_update.jsonl"), jl("r1_c4_local_split_tables.jsonl"), jl("r1_c5_sweep.jsonl")
@@ -77,7 +78,7 @@ Every number comes from `gpurun` runs on B200s of this pool.  The `.ncu-rep` fil
 | `r1_launches_bench_c2.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-overlap` |
 | `r1_ncu_kernels.json` | per-launch DRAM bytes / time / registers / occupancy of the two hot kernels from the `ncu --set full` capture of the same command (`bench.py` reads `roofline.traffic` from it) |
 | `r1_launches_bench_c2_zipf.csv`, `r1a_launches_bench_c2.csv` | launch lists for `--dist zipf` and for the FIRST correct version (before any tuning) |
-| `r1_bench_c2_n4_fused.json`, `r1_bench_c2_n8_fused.json`, `r1_bench_c2_n8_nccl.json` | torchrun bench lines at N = 4 / 8 |
+| `r1_bench_c2_n2_fused.json`, `..._n4_fused.json`, `..._n8_fused.json`, `..._n8_nccl.json` | torchrun bench lines at N = 2 / 4 / 8 |
 | `r1_ubench_random_rmw_ceiling.json` | `tools/ubench_rmw.cu`: what HBM delivers for random 512-byte RMW / reads |
 | `r1_c1_*.jsonl`, `r1_c3_*.jsonl`, `r1_c4_*.jsonl`, `r1_c5_sweep.jsonl` | `tools/bench_configs.py`: the other BASELINE configs |
 
@@ -128,18 +129,18 @@ DRAM-bound uniform case unchanged (0.98 ms) and sped the L2-bound Zipf forward u
 
 ## Multi-GPU (weak scaling: 26 tables per GPU, global batch 16384)
 
-| N | exchange | code state | ms/step | lookups/s | fwd+exchange / bwd exchange / index+update ms |
+| N | exchange | ms/step | lookups/s | vs N x 1-GPU | fwd+exchange / bwd exchange / index+update ms |
 |---|---|---|---|---|---|
-| 8 | fused NVLink stores | current | {n8['ms_per_step']:.2f} | **{n8['value']/1e9:.1f} G** | {n8['phases_ms']['fwd_lookup+exchange']:.2f} / {n8['phases_ms']['bwd_exchange']:.2f} / {n8['phases_ms']['index+update']:.2f} |
-| 4 | fused NVLink stores | earlier (update kernel 2.45 ms, no index! prefetch) | {n4['ms_per_step']:.2f} | {n4['value']/1e9:.1f} G | {n4['phases_ms']['fwd_lookup+exchange']:.2f} / {n4['phases_ms']['bwd_exchange']:.2f} / {n4['phases_ms']['index+update']:.2f} |
-| 8 | NCCL all-to-all + pack/unpack | earlier (same state as the N = 4 line) | {n8n['ms_per_step']:.2f} | {n8n['value']/1e9:.1f} G | {n8n['phases_ms']['fwd_lookup+exchange']:.2f} / {n8n['phases_ms']['bwd_exchange']:.2f} / {n8n['phases_ms']['index+update']:.2f} |
+| 1 | - | {U['ms_per_step']:.2f} | {U['value']/1e9:.2f} G | - | {ku['pooled_kernel']['ms']:.2f} / - / {ku['sgd_update_kernel']['ms'] + ku['index(make_pairs+radix sort+select)']['ms']:.2f} (index! mostly hidden) |
+| 2 | fused NVLink stores | {n2['ms_per_step']:.2f} | {n2['value']/1e9:.2f} G | {n2['value']/2/U['value']*100:.0f} % | {n2['phases_ms']['fwd_lookup+exchange']:.2f} / {n2['phases_ms']['bwd_exchange']:.2f} / {n2['phases_ms']['index+update']:.2f} |
+| 4 | fused NVLink stores | {n4['ms_per_step']:.2f} | {n4['value']/1e9:.1f} G | {n4['value']/4/U['value']*100:.0f} % | {n4['phases_ms']['fwd_lookup+exchange']:.2f} / {n4['phases_ms']['bwd_exchange']:.2f} / {n4['phases_ms']['index+update']:.2f} |
+| 8 | fused NVLink stores | {n8['ms_per_step']:.2f} | **{n8['value']/1e9:.1f} G** | {n8['value']/8/U['value']*100:.0f} % | {n8['phases_ms']['fwd_lookup+exchange']:.2f} / {n8['phases_ms']['bwd_exchange']:.2f} / {n8['phases_ms']['index+update']:.2f} |
+| 8 | NCCL all-to-all + pack/unpack (earlier code state: update 2.45 ms) | {n8n['ms_per_step']:.2f} | {n8n['value']/1e9:.1f} G | - | {n8n['phases_ms']['fwd_lookup+exchange']:.2f} / {n8n['phases_ms']['bwd_exchange']:.2f} / {n8n['phases_ms']['index+update']:.2f} |
 
-Current N = 8 vs 8 x the current 1-GPU step ({U['value']/1e9:.2f} G lookups/s): {n8['value']/8/U['value']*100:.0f} % weak-scaling efficiency.  In the earlier
-state (1-GPU 3.99 G lookups/s) the fused exchange reached 88 % at N = 8 (28.3 G) and 91 % at N = 4, the NCCL
-variant 79 %.  Per rank and direction the exchange moves 191 MB at N = 8; the fused backward scatter alone took
-0.31 ms (0.62 TB/s of the measured 0.77 TB/s link rate) -- 0.79 ms before the destinations were visited in
-rotated order (every rank storing into GPU 0 first).  e2e at N = 8 is host-bound: 8 ranks x 553 MB per step
-through one host = 39 ms.
+In the same (earlier) code state the fused exchange measured 3.85 ms/step at N = 8 against the NCCL variant's 4.33 ms.
+Per rank and direction the exchange moves 191 MB at N = 8; the fused backward scatter alone took 0.31 ms (0.62 TB/s of
+the measured 0.77 TB/s link rate) -- 0.79 ms before the destinations were visited in rotated order (every rank storing
+into GPU 0 first).  e2e at N = 8 is host-bound: 8 ranks x 553 MB per step through one host = 39 ms.
 
 ## Other BASELINE configs (`tools/bench_configs.py`)
 
