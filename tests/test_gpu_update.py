@@ -429,3 +429,26 @@ def test_index_sort_is_a_stable_sort(E, n, nrows, wide):
     assert np.array_equal(mp, order.astype(np.int32))
     nnz = int(_peek(v.nnz, 1, np.int64)[0])
     assert nnz == np.unique(I).size
+
+
+def test_strided_dynamic_table(E, O):
+    # a Dynamic SimpleEmbedding over a row-slice VIEW of a bigger matrix (leading dimension > featuresize):
+    # the reference's Dynamic columnpointer honours strides(A)[2] (src/simple.jl:52, src/EmbeddingTables.jl:83-85)
+    rng = np.random.default_rng(61)
+    big_h = rng.standard_normal((100, 300)).astype(np.float32)
+    big = E.DeviceArray.from_numpy(big_h)
+    for dim in (64, 20):                       # 16-byte and 8-byte aligned slices
+        view = big.rows(8, 8 + dim)
+        table = E.SimpleEmbedding(view)        # Dynamic
+        base = big_h[8:8 + dim].copy()
+        I = rng.integers(1, 301, (5, 200))
+        assert np.array_equal(E.lookup(table, I).numpy(), O.lookup(O.Table(base), I))
+        delta = rng.standard_normal((dim, 200)).astype(np.float32)
+        before = big.numpy().copy()
+        E.update_(E.Descent(0.1), table, E.SparseEmbeddingUpdate(E.Dynamic(), delta, I))
+        ref = O.Table(base.copy(order="F"))
+        O.update(ref, delta, I, 0.1)
+        after = big.numpy()
+        assert np.array_equal(after[8:8 + dim], ref.data)
+        assert np.array_equal(after[:8], before[:8]) and np.array_equal(after[8 + dim:], before[8 + dim:])  # neighbours untouched
+        big_h = after
