@@ -286,6 +286,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     overlap = not args.no_overlap
+    # nvidia-smi needs up to a second to deliver its first sample: start it before the warm-up so that it is
+    # sampling (every 20 ms) throughout the timed regions; stopped after the e2e region
+    clocks = ClockSampler(local)
+    clocks.__enter__()
     for _ in range(args.warmup):
         step(overlap=False)
         step(overlap=overlap)
@@ -293,8 +297,6 @@ def run_ours(args):
     K = args.steps
     # ---- the timed region: K steps, index! overlapped with the forward unless --no-overlap
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    clocks = ClockSampler(local)          # samples every 20 ms until the e2e region below has finished
-    clocks.__enter__()
     sync()
     start.record()
     for k in range(K):
@@ -436,19 +438,20 @@ def run_sharded(args, rank, world, local):
         dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)   # started before the warm-up (nvidia-smi needs ~1 s for its first sample),
+    clocks.__enter__()             # stopped after the e2e region
     for _ in range(args.warmup):
         step()
     sync()
     K = args.steps
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     end = torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        sync()
-        for k in range(K):
-            ev[k][0].record()
-            step(ev[k])
-        end.record()
-        sync()
+    sync()
+    for k in range(K):
+        ev[k][0].record()
+        step(ev[k])
+    end.record()
+    sync()
     t = torch.tensor([ev[0][0].elapsed_time(end) / K,
                       float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
                       float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
@@ -467,6 +470,7 @@ def run_sharded(args, rank, world, local):
     e1.record()
     sync()
     e2e = torch.tensor([max(e0.elapsed_time(e1) / K, (time.perf_counter() - t0) * 1e3 / K)], device="cuda", dtype=torch.float64)
+    clocks.__exit__(None, None, None)
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     e2e_ms = e2e.item()
 
