@@ -158,6 +158,9 @@ peak): {c1['step_us']:.0f} µs eager (host-enqueue bound: the Python mirror spen
 
 Chunked addressing costs nothing (one 32-bit divide per index, done by one lane).
 
+**Non-reducing gather** (K1; `tools/gather_check.py`: 26 tables x 1M rows, one index per output column, GPU time by
+graph replay), fraction of the measured peak: dim 16 / batch 16384: 0.36, dim 16 / batch 65536: 0.56, dim 64 / batch 16384: 0.69, dim 64 / batch 65536: 0.83, dim 128 / batch 16384: 0.85, dim 128 / batch 65536: 0.95, dim 256 / batch 16384: 0.96, dim 256 / batch 65536: 1.02.
+
 **update! over feature sizes** (C2's shape with dim varied: 26 tables x 1M rows, bag 32, batch 16384, uniform; dim 80
 is not a power of two -- 20 of a group's 32 lanes are active; dims 16-64 move 64-256-byte rows):
 
