@@ -86,6 +86,8 @@ class Indexer(AbstractIndexer):
         need = C.c_size_t()
         _lib.check(_lib.lib().etb_index_workspace_bytes(items_arr, n, C.byref(need)))
         if self.workspace is None or self.workspace.numel() < need.value:
+            if self.workspace is not None:
+                torch.cuda.synchronize()   # kernels on other streams may still read the old workspace
             self.workspace = torch.empty(need.value, dtype=torch.uint8, device="cuda")
 
     # --- host-side inspection (tests): the reference's `cumulative` / `map`, order-insensitive
