@@ -79,6 +79,7 @@ Every number comes from `gpurun` runs on B200s of this pool.  The `.ncu-rep` fil
 | `r1_ncu_kernels.json` | per-launch DRAM bytes / time / registers / occupancy of the two hot kernels from the `ncu --set full` capture of the same command (`bench.py` reads `roofline.traffic` from it) |
 | `r1_launches_bench_c2_zipf.csv`, `r1a_launches_bench_c2.csv` | launch lists for `--dist zipf` and for the FIRST correct version (before any tuning) |
 | `r1_bench_c2_n2_fused.json`, `..._n4_fused.json`, `..._n8_fused.json`, `..._n8_nccl.json` | torchrun bench lines at N = 2 / 4 / 8 |
+| `r1_sass_excerpts.txt` | `cuobjdump -sass` of the two hot kernels: the independent `LDG.E.128` of a batch issued back to back before the ordered `FADD` / `FFMA` chain |
 | `r1_ubench_random_rmw_ceiling.json` | `tools/ubench_rmw.cu`: what HBM delivers for random 512-byte RMW / reads |
 | `r1_c1_*.jsonl`, `r1_c3_*.jsonl`, `r1_c4_*.jsonl`, `r1_c5_sweep.jsonl` | `tools/bench_configs.py`: the other BASELINE configs |
 
