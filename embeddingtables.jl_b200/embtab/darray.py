@@ -80,6 +80,14 @@ class DeviceArray:
         buf = torch.as_tensor(raw, device="cuda")
         return DeviceArray(buf, shape, 0, ld_, dtype)
 
+    @staticmethod
+    def mapped(host: np.ndarray) -> "DeviceArray":
+        """Device view of a PAGE-LOCKED host array (see pinned_empty).  Pinned memory is device-addressable
+        under unified addressing, so a kernel can store its result into it / load its operand from it over
+        PCIe without a staging copy.  No ownership: keep `host` alive."""
+        assert host.flags.f_contiguous or host.ndim <= 1, "Julia (column-major) layout expected"
+        return DeviceArray.from_pointer(host.ctypes.data, host.shape, host.dtype)
+
     def similar(self, dtype=None, shape=None) -> "DeviceArray":
         """Julia `similar(example(A), T, dims)` (reference src/lookup.jl:20-22)."""
         return DeviceArray.empty(self.shape if shape is None else shape, dtype or self.dtype,

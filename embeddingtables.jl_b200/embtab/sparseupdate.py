@@ -215,7 +215,10 @@ def _flags(table) -> int:
 
 
 def _apply(tables, grads, indexer, eta):
-    """update!(table, update, indexer, alpha): apply an already-indexed update."""
+    """update!(table, update, indexer, alpha): apply an already-indexed update.  The cotangent applied is
+    the one of the updates passed HERE (reference src/sparseupdate.jl:131-154 reads `update.delta`); the
+    indexer only has to hold index! of the same index arrays."""
+    items = [_update_item(t, g) for t, g in zip(tables, grads)]
     if isinstance(indexer, IndexerView):
         base = indexer.I
         view = _lib.IndexView.from_buffer_copy(base.view)
@@ -224,7 +227,8 @@ def _apply(tables, grads, indexer, eta):
         base, view = indexer, indexer.view
     flags = _lib.UPDATE_SPLIT_LONG if _ORDER["mode"] == "split" else 0   # FMA travels per item
     stream = C.c_void_p(current_stream_ptr())
-    _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(tables), float(eta), flags, stream))
+    base._items = (_lib.UpdateItem * len(items))(*items)
+    _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(items), float(eta), flags, stream))
 
 
 def update_table_(table, update: SparseEmbeddingUpdate, indexer, alpha, nontemporal=True, *args):
@@ -259,14 +263,11 @@ def update_(opt: Descent, table, grad, indexer=None, nontemporal=True, *args, nu
 
 
 def _consume_prefetch(indexer: Indexer, tables, grads) -> bool:
-    """True if `indexer` holds a prefetch_index result for exactly these index arrays: wait for it and
-    rebuild the item descriptors with the real cotangents."""
+    """True if `indexer` holds a prefetch_index result for exactly these index arrays: wait for it."""
     if indexer._prefetched is None or indexer._prefetched != [g.indices.ptr for g in grads]:
         return False
     torch.cuda.current_stream().wait_event(indexer._event)
-    items = [_update_item(t, g) for t, g in zip(tables, grads)]
-    indexer._items = (_lib.UpdateItem * len(items))(*items)
-    indexer._event, indexer._prefetched = None, None
+    indexer._event, indexer._prefetched = None, None   # _apply builds the items from the real cotangents
     return True
 
 

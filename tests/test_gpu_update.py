@@ -452,3 +452,50 @@ def test_strided_dynamic_table(E, O):
         assert np.array_equal(after[8:8 + dim], ref.data)
         assert np.array_equal(after[:8], before[:8]) and np.array_equal(after[8 + dim:], before[8 + dim:])  # neighbours untouched
         big_h = after
+
+
+def test_update_applies_the_cotangent_passed_to_update(E, O):
+    # update!(table, update, indexer, alpha) reads update.delta (reference src/sparseupdate.jl:131-154):
+    # an indexer filled for one update may be reused with ANOTHER cotangent over the same indices
+    rng = np.random.default_rng(71)
+    base = rng.standard_normal((32, 200)).astype(np.float32)
+    I = rng.integers(1, 201, (4, 150))
+    Id = E.as_device_indices(I)
+    d1 = rng.standard_normal((32, 150)).astype(np.float32)
+    d2 = rng.standard_normal((32, 150)).astype(np.float32)
+    table = E.SimpleEmbedding(base.copy(), E.Static(32))
+    ix = E.Indexer()
+    E.index_(ix, table, E.SparseEmbeddingUpdate(E.Static(32), d1, Id))
+    E.update_table_(table, E.SparseEmbeddingUpdate(E.Static(32), d2, Id), ix, 0.25)
+    ref = O.Table(base.copy(order="F"), static=True)
+    O.update(ref, d2, I, 0.25)
+    assert np.array_equal(table.to_numpy(), ref.data)
+
+
+def test_host_mapped_result_and_cotangent(E, O):
+    # page-locked host buffers are device-addressable: the forward may store its result straight into one
+    # and update! may read its cotangent straight from one (no staging copy); results are unchanged
+    import torch
+    rng = np.random.default_rng(72)
+    base = [rng.standard_normal((64, 500)).astype(np.float32) for _ in range(2)]
+    I = rng.integers(1, 501, (8, 256, 2))
+    Id = E.as_device_indices(I)
+    tables = [E.SimpleEmbedding(b.copy(), E.Static(64)) for b in base]
+    out_h = E.pinned_empty((16 + 128, 256), np.float32)
+    out_h[...] = -1.0
+    out_m = E.DeviceArray.mapped(out_h)
+    E.maplookup_(E.PreallocationStrategy(16), out_m, tables, Id)
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert np.array_equal(out_h[16 + 64 * k:16 + 64 * (k + 1)], O.lookup(O.Table(base[k], static=True), I[:, :, k]))
+    assert np.all(out_h[:16] == -1.0)                          # the prepended rows are the caller's
+    delta_h = E.pinned_empty((16 + 128, 256), np.float32)
+    delta_h[...] = rng.standard_normal(delta_h.shape).astype(np.float32)
+    delta_m = E.DeviceArray.mapped(delta_h)
+    slicer = E.Slicer(17, 1, delta_m)
+    grads = [E.SparseEmbeddingUpdate(E.Static(64), slicer(64), i) for i in E.colwrap(Id)]
+    E.update_(E.Descent(0.5), tables, grads, [E.Indexer()])
+    for k in range(2):
+        ref = O.Table(base[k].copy(order="F"), static=True)
+        O.update(ref, np.asfortranarray(delta_h[16 + 64 * k:16 + 64 * (k + 1)]), I[:, :, k], 0.5)
+        assert np.array_equal(tables[k].to_numpy(), ref.data)
