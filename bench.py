@@ -236,12 +236,20 @@ def run_ours(args):
         if events: events[3].record()
 
     # e2e: every step copies ITS indices and cotangent in from pinned host memory and its feature
-    # matrix out.  The only cross-step pipelining is the standard input double buffer: step k+1's
+    # matrix out.  Across steps the only pipelining is the standard input double buffer: step k+1's
     # indices are uploaded on a copy stream while step k's result is downloaded (H2D and D2H use
-    # different copy engines).  Within a step the dependency chain is kept: forward -> result on the
-    # host -> cotangent from the host -> update.
+    # different copy engines).  Within a step the dependency chain is kept -- forward -> result on the
+    # host -> cotangent from the host -> update -- and pipelined at its two PCIe legs:
+    #   * the forward runs in E2E_CHUNKS column chunks, chunk c going to the host while chunk c+1 is looked up;
+    #   * the cotangent comes in as E2E_GROUPS row slices (one group of tables each, a strided 2-D copy), and
+    #     each group's update! (its own Indexer, index! prefetched beside the forward) runs as soon as its
+    #     slice has landed, while the next slice is still on the wire.
     copy_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
     E2E_CHUNKS = 4
+    E2E_GROUPS = max(1, min(NT, int(os.environ.get("ETB_E2E_GROUPS", "13"))))
+    bounds = [round(g * NT / E2E_GROUPS) for g in range(E2E_GROUPS + 1)]
+    groups = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    group_ix = [E.Indexer() for _ in groups]
     I_buf = [I_dev, E.DeviceArray.empty((BAG, BATCH, NT), np.int64)]
     Is_buf = [Is, list(E.colwrap(I_buf[1]))]
     idx_ready = [None, None]
@@ -263,7 +271,8 @@ def run_ours(args):
         main = torch.cuda.current_stream()
         main.wait_event(idx_ready[slot])
         idx_ready[slot] = None
-        E.prefetch_index(indexer, tables, Is_buf[slot])   # side stream: overlaps forward + PCIe copies
+        for (a, b), ix in zip(groups, group_ix):          # side stream: overlaps forward + PCIe copies
+            E.prefetch_index(ix, tables[a:b], Is_buf[slot][a:b])
         # forward in E2E_CHUNKS column chunks: chunk c's result goes to the host (D2H stream) while chunk
         # c+1 is being looked up
         for c in range(E2E_CHUNKS):
@@ -273,12 +282,21 @@ def run_ours(args):
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
                 out_dev.cols(c0, c1).download(out_pinned[:, c0:c1])   # D2H: the step's result, chunk c
-        upload_indices(1 - slot)                          # next step's indices, behind this step's D2H
-        main.wait_stream(d2h_stream)                      # the host has the whole feature matrix
-        delta_dev.upload(delta_pinned)                    # H2D: the upstream cotangent
+        upload_indices(1 - slot)                          # next step's indices, beside this step's D2H
+        # H2D: the upstream cotangent, once the host has the whole feature matrix; group g's rows
+        # (the first slice also carries the PREPEND rows of the dense part: the whole matrix is copied)
+        landed = []
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_stream(d2h_stream)
+            for a, b in groups:
+                r0, r1 = (0 if a == 0 else PREPEND + a * DIM), PREPEND + b * DIM
+                delta_dev.rows(r0, r1).upload(delta_pinned[r0:r1])
+                landed.append(copy_stream.record_event())
         slicer = E.Slicer(PREPEND + 1, 1, delta_dev)
         grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is_buf[slot]]
-        E.update_(opt, tables, grads, [indexer])
+        for (a, b), ix, ev in zip(groups, group_ix, landed):
+            main.wait_event(ev)
+            E.update_(opt, tables[a:b], grads[a:b], [ix])
         buf_free[slot] = main.record_event()
         e2e_state["k"] = k + 1
 
@@ -367,7 +385,10 @@ def run_ours(args):
                    "distinct_rows_per_table_mean": u_sum / NT},
         "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
-                "d2h_bytes_per_step": int(out_pinned.nbytes)},
+                "d2h_bytes_per_step": int(out_pinned.nbytes),
+                "pipeline": "indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent in %d "
+                            "table-group row slices (2-D H2D), each group's update! as its slice lands"
+                            % (E2E_CHUNKS, len(groups))},
         "gpu_launches": gpu_launches,
         "launches_per_step": launches,
         "clocks": clocks.result,

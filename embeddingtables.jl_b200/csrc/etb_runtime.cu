@@ -116,6 +116,26 @@ int32_t etb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
     return ETB_OK;
 }
 
+int32_t etb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes,
+                         size_t height, void* stream) {
+    if (width_bytes == 0 || height == 0) return ETB_OK;
+    ETB_REQUIRE(dst && src_host, "etb_memcpy2d_h2d: null pointer");
+    ETB_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "etb_memcpy2d_h2d: pitch smaller than the run");
+    ETB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src_host, src_pitch, width_bytes, height, cudaMemcpyHostToDevice,
+                               (cudaStream_t)stream));
+    return ETB_OK;
+}
+
+int32_t etb_memcpy2d_d2h(void* dst_host, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                         size_t height, void* stream) {
+    if (width_bytes == 0 || height == 0) return ETB_OK;
+    ETB_REQUIRE(dst_host && src, "etb_memcpy2d_d2h: null pointer");
+    ETB_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "etb_memcpy2d_d2h: pitch smaller than the run");
+    ETB_CUDA(cudaMemcpy2DAsync(dst_host, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+    return ETB_OK;
+}
+
 int32_t etb_memset(void* dst, int32_t byte, size_t bytes, void* stream) {
     if (bytes == 0) return ETB_OK;
     ETB_REQUIRE(dst, "etb_memset: null pointer");

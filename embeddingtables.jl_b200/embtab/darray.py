@@ -164,17 +164,31 @@ class DeviceArray:
 
     def upload(self, host: np.ndarray) -> "DeviceArray":
         """Asynchronous host->device copy on the current stream.  `host` holds this array's
-        elements in column-major memory order (e.g. a pinned buffer from `pinned_empty`); the
-        copy is truly asynchronous only from pinned memory."""
-        assert self.is_dense and host.dtype == self.dtype and host.size == int(np.prod(self.shape))
-        _lib.check(_lib.lib().etb_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, current_stream_ptr()))
+        elements in column-major memory order (e.g. a pinned buffer from `pinned_empty`, or a row-slice
+        view of one); the copy is truly asynchronous only from pinned memory.  Row-slice views on either
+        side go as one strided (2-D) copy, without staging."""
+        assert host.dtype == self.dtype and host.size == int(np.prod(self.shape))
+        hp = _host_pitch(host)
+        if self.is_dense and hp is None:
+            _lib.check(_lib.lib().etb_memcpy_h2d(self.ptr, host.ctypes.data, host.nbytes, current_stream_ptr()))
+        else:
+            assert self.ndim == 2 and host.shape == self.shape
+            w = self.shape[0] * self.itemsize
+            _lib.check(_lib.lib().etb_memcpy2d_h2d(self.ptr, self.ld * self.itemsize, host.ctypes.data, hp or w, w,
+                                                   self.shape[1], current_stream_ptr()))
         return self
 
     def download(self, host: np.ndarray) -> np.ndarray:
         """Asynchronous device->host copy on the current stream (synchronise before reading)."""
-        assert self.is_dense and host.dtype == self.dtype and host.size == int(np.prod(self.shape))
-        assert host.flags.f_contiguous or host.flags.c_contiguous, "download target must be one contiguous block"
-        _lib.check(_lib.lib().etb_memcpy_d2h(host.ctypes.data, self.ptr, host.nbytes, current_stream_ptr()))
+        assert host.dtype == self.dtype and host.size == int(np.prod(self.shape))
+        hp = _host_pitch(host)
+        if self.is_dense and hp is None:
+            _lib.check(_lib.lib().etb_memcpy_d2h(host.ctypes.data, self.ptr, host.nbytes, current_stream_ptr()))
+        else:
+            assert self.ndim == 2 and host.shape == self.shape
+            w = self.shape[0] * self.itemsize
+            _lib.check(_lib.lib().etb_memcpy2d_d2h(host.ctypes.data, hp or w, self.ptr, self.ld * self.itemsize, w,
+                                                   self.shape[1], current_stream_ptr()))
         return host
 
     def fill(self, v):
@@ -200,6 +214,15 @@ class DeviceArray:
 
     def __repr__(self):
         return f"DeviceArray{self.shape}<{self.dtype}, ld={self.ld}>"
+
+
+def _host_pitch(host: np.ndarray):
+    """None for one contiguous block; the column pitch in bytes for a row-slice view of a column-major matrix."""
+    if host.flags.f_contiguous or host.flags.c_contiguous:
+        return None
+    assert host.ndim == 2 and host.strides[0] == host.itemsize and host.strides[1] >= host.shape[0] * host.itemsize, \
+        "host array must be contiguous or a row-slice view of a column-major matrix"
+    return host.strides[1]
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:

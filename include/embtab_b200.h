@@ -146,6 +146,13 @@ int32_t etb_free_host(void* ptr_host);
 int32_t etb_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream);
 int32_t etb_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream);
 int32_t etb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+/* Strided (2-D) copies: `height` runs of `width_bytes` contiguous bytes, run k at base + k * pitch.  This is the
+ * row-slice view of a column-major matrix -- e.g. one table's rows of the concatenated cotangent
+ * (reference src/utils.jl:289-302 Slicer, src/lookup.jl:374-389) -- moved without staging. */
+int32_t etb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes,
+                         size_t height, void* stream);
+int32_t etb_memcpy2d_d2h(void* dst_host, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                         size_t height, void* stream);
 int32_t etb_memset(void* dst, int32_t byte, size_t bytes, void* stream);
 int32_t etb_stream_create(void** stream_host);
 int32_t etb_stream_sync(void* stream);

@@ -302,3 +302,26 @@ def test_direct_c_entry_points(E, O):
     for p in ptrs:
         _lib.check(lib.etb_free(p))
     _lib.check(lib.etb_stream_destroy(stream))
+
+
+def test_strided_upload_download_of_row_slices(E):
+    # one table's rows of a concatenated (column-major) matrix move as a single 2-D copy, both directions,
+    # without touching the neighbouring rows (etb_memcpy2d_h2d / etb_memcpy2d_d2h)
+    import torch
+    rng = np.random.default_rng(5)
+    host = E.pinned_empty((40, 33), np.float32)
+    host[...] = rng.standard_normal((40, 33)).astype(np.float32)
+    dev = E.DeviceArray.zeros((40, 33))
+    dev.rows(8, 24).upload(host[8:24])                       # strided on both sides
+    torch.cuda.synchronize()
+    got = dev.numpy()
+    assert np.array_equal(got[8:24], host[8:24]) and np.all(got[:8] == 0) and np.all(got[24:] == 0)
+    dense = np.asfortranarray(rng.standard_normal((16, 33)).astype(np.float32))
+    dev.rows(24, 40).upload(dense)                           # contiguous host, strided device
+    back = E.pinned_empty((40, 33), np.float32)
+    back[...] = -7.0
+    dev.rows(24, 40).download(back[2:18])                    # strided device, strided host
+    torch.cuda.synchronize()
+    assert np.array_equal(back[2:18], dense) and np.all(back[:2] == -7.0) and np.all(back[18:] == -7.0)
+    with pytest.raises(AssertionError):
+        dev.rows(0, 8).upload(host[::2][:8])                 # not a row-slice view
