@@ -164,7 +164,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"], "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -399,7 +399,7 @@ def run_ours(args):
         "fwd_bwd_sgd_frac_of_peak": (fwd_bytes + upd_total_bytes) / (ms_per_step * 1e6) / peak,
         "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def run_sharded(args, rank, world, local):
@@ -447,6 +447,9 @@ def run_sharded(args, rank, world, local):
         if events: events[3].record()
         launches[0] = n
 
+    # e2e: indices and cotangent in from pinned host memory, this rank's feature-matrix columns out, every step.
+    # Not pipelined: with N ranks pulling through one host the PCIe legs are host-bound (double-buffering the
+    # index upload was measured at N = 2 and changed nothing).
     def step_e2e():
         I_dev.upload(idx_pinned)
         ens.forward(I_dev)
@@ -522,11 +525,25 @@ def run_sharded(args, rank, world, local):
                        "note": "phase times include the lookup / pack kernels; see profiles/ for the split"},
             "cpu_baseline": None,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit_line(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    print(json.dumps(line), file=_JSON_OUT or sys.stdout, flush=True)
+
+
 def main():
+    # Libraries print to stdout behind our back (NCCL's "NCCL version ..." banner under NCCL_DEBUG=VERSION/WARN):
+    # keep the real stdout for the JSON line and point file descriptor 1 at stderr for everything else.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
