@@ -1,5 +1,7 @@
 // etb_common.cuh -- shared host/device helpers of libembtab_b200 (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -34,8 +36,11 @@ int32_t& launch_counter();  // thread-local: kernels launched by the current API
         ETB_CUDA(cudaGetLastError());                                                      \
     } while (0)
 
-inline size_t elt_bytes(int32_t elt) { return (elt == ETB_F32 || elt == ETB_I32) ? 4 : 8; }
-inline bool elt_valid(int32_t elt) { return elt >= ETB_F32 && elt <= ETB_I64; }
+inline size_t elt_bytes(int32_t elt) {
+    return (elt == ETB_F16 || elt == ETB_BF16) ? 2 : ((elt == ETB_F32 || elt == ETB_I32) ? 4 : 8);
+}
+inline bool elt_valid(int32_t elt) { return elt >= ETB_F32 && elt <= ETB_BF16; }
+inline bool elt_is_float(int32_t elt) { return elt == ETB_F32 || elt == ETB_F64 || elt == ETB_F16 || elt == ETB_BF16; }
 inline bool idx_elt_valid(int32_t e) { return e == ETB_I32 || e == ETB_I64; }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
@@ -100,6 +105,80 @@ struct alignas(VB) Vec {
     static constexpr int NE = VB / (int)sizeof(T);
     T e[NE];
 };
+
+// Storage type -> arithmetic type.  Half-precision tables (ETB_F16 / ETB_BF16, an extension: the reference has
+// Float32/Float64/integer tables only) are summed and updated in Float32 and rounded to nearest-even once, when
+// the result is stored; every other type computes in itself.
+template <typename T>
+struct AccOf {
+    using type = T;
+};
+template <>
+struct AccOf<__half> {
+    using type = float;
+};
+template <>
+struct AccOf<__nv_bfloat16> {
+    using type = float;
+};
+template <typename T>
+using acc_t = typename AccOf<T>::type;
+
+template <typename T>
+__device__ __forceinline__ acc_t<T> to_acc(T x) {
+    return x;
+}
+template <>
+__device__ __forceinline__ float to_acc<__half>(__half x) {
+    return __half2float(x);
+}
+template <>
+__device__ __forceinline__ float to_acc<__nv_bfloat16>(__nv_bfloat16 x) {
+    return __bfloat162float(x);
+}
+template <typename T>
+__device__ __forceinline__ T from_acc(acc_t<T> x) {
+    return x;
+}
+template <>
+__device__ __forceinline__ __half from_acc<__half>(float x) {
+    return __float2half_rn(x);
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16>(float x) {
+    return __float2bfloat16_rn(x);
+}
+
+// accumulator twin of Vec<T, VB>: the same NE elements, in the arithmetic type (identical to Vec for
+// Float32/Float64/integers, twice the bytes for the half types)
+template <typename T, int VB>
+struct alignas(VB) AccVec {
+    static constexpr int NE = VB / (int)sizeof(T);
+    acc_t<T> e[NE];
+};
+
+template <typename T, int VB>
+__device__ __forceinline__ void acc_add(AccVec<T, VB>& acc, const Vec<T, VB>& v) {
+#pragma unroll
+    for (int k = 0; k < Vec<T, VB>::NE; ++k) acc.e[k] = acc.e[k] + to_acc<T>(v.e[k]);
+}
+template <typename T, int VB>
+__device__ __forceinline__ void acc_add(AccVec<T, VB>& acc, const AccVec<T, VB>& v) {
+#pragma unroll
+    for (int k = 0; k < Vec<T, VB>::NE; ++k) acc.e[k] = acc.e[k] + v.e[k];
+}
+template <typename T, int VB>
+__device__ __forceinline__ void acc_fill(AccVec<T, VB>& acc, acc_t<T> x) {
+#pragma unroll
+    for (int k = 0; k < Vec<T, VB>::NE; ++k) acc.e[k] = x;
+}
+template <typename T, int VB>
+__device__ __forceinline__ Vec<T, VB> acc_round(const AccVec<T, VB>& acc) {
+    Vec<T, VB> out;
+#pragma unroll
+    for (int k = 0; k < Vec<T, VB>::NE; ++k) out.e[k] = from_acc<T>(acc.e[k]);
+    return out;
+}
 
 // Read-only row loads through the non-coherent path with the DEFAULT L2 policy.  Measured on
 // B200 (profiles/r1a): adding `.L1::no_allocate` makes the sectors evict_first in L2, and rows

@@ -63,12 +63,6 @@ __device__ __forceinline__ double additive_identity<double>() {
     return -0.0;
 }
 
-template <typename T, int VB>
-__device__ __forceinline__ void vec_add(Vec<T, VB>& acc, const Vec<T, VB>& v) {
-#pragma unroll
-    for (int k = 0; k < Vec<T, VB>::NE; ++k) acc.e[k] = acc.e[k] + v.e[k];
-}
-
 // ------------------------------------------------------------------------------------ K2/K3
 // Occupancy over per-warp depth (measured, profiles/README.md): with 4 rows in flight per lane the VPL = 1
 // kernel needs 32 registers -> 64 warps/SM; uniform C2 is at the DRAM limit either way (0.98 ms), the
@@ -81,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, (VPL == 1 && !DEEP) ? (sizeof(T) == 
 pooled_kernel(const __grid_constant__ LookupParams P) {
     constexpr int U = (VPL == 1 && !DEEP) ? 4 : ((8 / VPL) > 1 ? (8 / VPL) : 1);  // row loads in flight per lane batch
     using V = Vec<T, VB>;
+    using A = AccVec<T, VB>;  // == V except for half-precision tables (Float32 accumulation)
     const LookupDesc& d = P.item[blockIdx.y];
     const int G = P.G;
     const int nvec = P.nvec;
@@ -102,11 +97,9 @@ pooled_kernel(const __grid_constant__ LookupParams P) {
         // Seed with the additive identity that leaves the first row's bits untouched:
         // (-0.0) + x == x for every x (incl. x = +-0), so this equals "accumulator = first
         // row" of the reference (src/lookup.jl:139-140) without a special first iteration.
-        V acc[VPL];
+        A acc[VPL];
 #pragma unroll
-        for (int p = 0; p < VPL; ++p)
-#pragma unroll
-            for (int k = 0; k < V::NE; ++k) acc[p].e[k] = additive_identity<T>();
+        for (int p = 0; p < VPL; ++p) acc_fill(acc[p], additive_identity<acc_t<T>>());
         for (uint32_t i0 = 0; i0 < bag; i0 += G) {
             const int m = (int)min((uint32_t)G, bag - i0);
             // one coalesced index load per group; each lane resolves one row address
@@ -124,20 +117,23 @@ pooled_kernel(const __grid_constant__ LookupParams P) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
 #pragma unroll
-                        for (int p = 0; p < VPL; ++p) vec_add(acc[p], v[u][p]);
+                        for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[u][p]);
                 } else {  // ragged tail: the clamped duplicates are loaded but not added
 #pragma unroll
                     for (int u = 0; u < U; ++u)
                         if (j0 + u < m)
 #pragma unroll
-                            for (int p = 0; p < VPL; ++p) vec_add(acc[p], v[u][p]);
+                            for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[u][p]);
                 }
             }
         }
 #pragma unroll
         for (int p = 0; p < VPL; ++p) {
             const int v = pass0 + gl + p * G;
-            if (active && v < nvec) st_stream<VB>(out + (size_t)v * VB, &acc[p]);
+            if (active && v < nvec) {
+                const V res = acc_round(acc[p]);
+                st_stream<VB>(out + (size_t)v * VB, &res);
+            }
         }
     }
 }
@@ -174,19 +170,20 @@ pooled_smallbag_kernel(const __grid_constant__ LookupParams P) {
     (void)nvec;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        V acc[VPL];
+        AccVec<T, VB> acc[VPL];
 #pragma unroll
-        for (int p = 0; p < VPL; ++p)
-#pragma unroll
-            for (int k = 0; k < V::NE; ++k) acc[p].e[k] = additive_identity<T>();
+        for (int p = 0; p < VPL; ++p) acc_fill(acc[p], additive_identity<acc_t<T>>());
 #pragma unroll
         for (int i = 0; i < BAG; ++i)
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) vec_add(acc[p], v[c * BAG + i][p]);
+            for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[c * BAG + i][p]);
         if (col0 + c < d.batch) {
             char* out = d.dst + (size_t)(col0 + c) * d.ld_dst_bytes;
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) st_stream<VB>(out + (size_t)(gl + p * G) * VB, &acc[p]);
+            for (int p = 0; p < VPL; ++p) {
+                const V res = acc_round(acc[p]);
+                st_stream<VB>(out + (size_t)(gl + p * G) * VB, &res);
+            }
         }
     }
 }
@@ -258,6 +255,8 @@ static int pick_vb(const etb_lookup_item& it) {
             aligned_to(it.dst, vb))
             return (int)vb;
     }
+    if (es == 2)  // half-precision rows must at least be 4-byte aligned (even dim and leading dimensions)
+        return (rowbytes % 4 == 0 && stride % 4 == 0 && ldd % 4 == 0 && aligned_to(it.table.base, 4) && aligned_to(it.dst, 4)) ? 4 : 0;
     return (int)es == 8 ? 8 : 4;
 }
 
@@ -267,6 +266,10 @@ static LookupClass classify(const etb_lookup_item& it) {
     c.pooled = it.bag > 0;
     c.idx_elt = it.idx_elt;
     c.vb = pick_vb(it);
+    if (c.vb == 0) {  // misaligned half-precision rows: rejected by the caller
+        c.nvec = c.G = c.vpl = 0;
+        return c;
+    }
     c.nvec = (int)((size_t)it.table.dim * elt_bytes(it.table.elt) / c.vb);
     c.G = std::min(32, pow2ceil(c.nvec));
     const int per_lane = (c.nvec + c.G - 1) / c.G;
@@ -289,7 +292,7 @@ static cudaError_t launch_pooled_vpl(int vpl, dim3 grid, cudaStream_t s, const L
 
 template <typename T, typename IdxT>
 static cudaError_t launch_pooled_vb(const LookupClass& c, dim3 grid, cudaStream_t s, const LookupParams& P) {
-    if constexpr (sizeof(T) == 4) {
+    if constexpr (sizeof(T) <= 4) {
         if (c.vb == 4) return launch_pooled_vpl<T, 4, IdxT>(c.vpl, grid, s, P);
     }
     if (c.vb == 8) return launch_pooled_vpl<T, 8, IdxT>(c.vpl, grid, s, P);
@@ -323,6 +326,8 @@ static int launch_smallbag(const LookupClass& c, int bag, uint32_t max_batch, in
         case ETB_F32: return launch_smallbag_t<float, IdxT>(c, bag, max_batch, n, s, P, err);
         case ETB_F64: return launch_smallbag_t<double, IdxT>(c, bag, max_batch, n, s, P, err);
         case ETB_I32: return launch_smallbag_t<uint32_t, IdxT>(c, bag, max_batch, n, s, P, err);
+        case ETB_F16: return launch_smallbag_t<__half, IdxT>(c, bag, max_batch, n, s, P, err);
+        case ETB_BF16: return launch_smallbag_t<__nv_bfloat16, IdxT>(c, bag, max_batch, n, s, P, err);
         default: return launch_smallbag_t<unsigned long long, IdxT>(c, bag, max_batch, n, s, P, err);
     }
 }
@@ -333,6 +338,8 @@ static cudaError_t launch_pooled(const LookupClass& c, dim3 grid, cudaStream_t s
         case ETB_F32: return launch_pooled_vb<float, IdxT>(c, grid, s, P);
         case ETB_F64: return launch_pooled_vb<double, IdxT>(c, grid, s, P);
         case ETB_I32: return launch_pooled_vb<uint32_t, IdxT>(c, grid, s, P);  // Julia ints wrap
+        case ETB_F16: return launch_pooled_vb<__half, IdxT>(c, grid, s, P);
+        case ETB_BF16: return launch_pooled_vb<__nv_bfloat16, IdxT>(c, grid, s, P);
         default: return launch_pooled_vb<unsigned long long, IdxT>(c, grid, s, P);
     }
 }
@@ -374,6 +381,8 @@ static int32_t maplookup_impl(const etb_lookup_item* items, int32_t n_items, cud
         ETB_REQUIRE(it.ld_dst >= it.table.dim, "etb_maplookup: item %d: ld_dst (%lld) < dim (%d)", i, (long long)it.ld_dst, it.table.dim);
         ETB_REQUIRE(it.bag == 0 || (it.ld_idx >= it.bag && it.ld_idx <= 0xffffffffll), "etb_maplookup: item %d: ld_idx (%lld) < bag (%lld)", i, (long long)it.ld_idx, (long long)it.bag);
         cls[i] = classify(it);
+        if (cls[i].vb == 0)
+            return fail(ETB_ERR_UNSUPPORTED, "etb_maplookup: item %d: half-precision rows must be 4-byte aligned (even dim, ld, ld_dst)", i);
     }
     static thread_local LookupParams P;  // 7 KB: keep it off the stack
     for (int i = 0; i < n_items; ++i) {

@@ -233,7 +233,8 @@ static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexL
         ETB_REQUIRE(it.bag == 0 || it.ld_idx >= it.bag, "etb_index: item %d: ld_idx < bag", i);
         n_total += it.batch * (it.bag ? it.bag : 1);
         max_rows = std::max(max_rows, it.table.nrows);
-        max_row_bytes = std::max(max_row_bytes, (size_t)it.table.dim * elt_bytes(it.table.elt));
+        // partial rows of long buckets are kept in the arithmetic type (Float32 for the half types)
+        max_row_bytes = std::max(max_row_bytes, (size_t)it.table.dim * std::max<size_t>(4, elt_bytes(it.table.elt)));
     }
     ETB_REQUIRE(n_total < 0x7fffffffll, "etb_index: %lld occurrences exceed the 2^31 limit of one call", (long long)n_total);
     L.n_total = n_total;
@@ -335,6 +336,24 @@ __device__ __forceinline__ double sgd_epilogue<double>(double row, double acc, d
     return fma ? __fma_rn(-eta, acc, row) : __dsub_rn(row, __dmul_rn(eta, acc));
 }
 
+// table element in, table element out; arithmetic in acc_t<T> (Float32 for the half types, one rounding at the end)
+template <typename T>
+__device__ __forceinline__ T sgd_apply(T row, acc_t<T> acc, acc_t<T> eta, bool fma) {
+    return from_acc<T>(sgd_epilogue<acc_t<T>>(to_acc<T>(row), acc, eta, fma));
+}
+
+// partial sums of long buckets are rows of AccVec (arithmetic type): AS = sizeof(AccVec) / VB pieces of VB bytes
+template <typename T, int VB>
+__device__ __forceinline__ void ld_acc(AccVec<T, VB>& a, const char* p) {
+#pragma unroll
+    for (int k = 0; k < (int)sizeof(AccVec<T, VB>) / VB; ++k) ld_plain<VB>((char*)&a + k * VB, p + k * VB);
+}
+template <typename T, int VB>
+__device__ __forceinline__ void st_acc(char* p, const AccVec<T, VB>& a) {
+#pragma unroll
+    for (int k = 0; k < (int)sizeof(AccVec<T, VB>) / VB; ++k) st_plain<VB>(p + k * VB, (const char*)&a + k * VB);
+}
+
 __device__ __forceinline__ unsigned group_mask(int G, int lane) {
     return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane & ~(G - 1)));
 }
@@ -349,7 +368,7 @@ __device__ __forceinline__ const char* shfl_ptr_mask(unsigned mask, const char* 
 // acc += delta[:, map[i]] for i in [i0, stop), strictly in order, U rows in flight.
 // All lanes of the calling group are converged; shuffles stay inside the group.
 template <typename T, int VB, int VPL, int U>
-__device__ __forceinline__ void accumulate_members(Vec<T, VB> (&acc)[VPL], const UpdDesc& d, const int32_t* map,
+__device__ __forceinline__ void accumulate_members(AccVec<T, VB> (&acc)[VPL], const UpdDesc& d, const int32_t* map,
                                                    int64_t i0, int64_t stop, const int (&vi)[VPL], int G, int gl,
                                                    int lane, unsigned gmask) {
     using V = Vec<T, VB>;
@@ -369,9 +388,7 @@ __device__ __forceinline__ void accumulate_members(Vec<T, VB> (&acc)[VPL], const
             for (int w = 0; w < U; ++w)
                 if (j0 + w < m)
 #pragma unroll
-                    for (int p = 0; p < VPL; ++p)
-#pragma unroll
-                        for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
+                    for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[w][p]);
         }
     }
 }
@@ -427,7 +444,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
     const unsigned gmask = group_mask(G, lane);
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
-    const T eta = (T)P.eta;  // convert(eltype(table), opt.eta), reference src/sparseupdate.jl:173
+    const acc_t<T> eta = (acc_t<T>)P.eta;  // convert(eltype(table), opt.eta), reference src/sparseupdate.jl:173
 
     int64_t s_begin = 0, s_end = nnz;
     if (P.num_splits > 0) {  // cumulative has nnz+1 entries; split_size = cdiv(nnz+1, num_splits)
@@ -491,11 +508,11 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                     if (k0 + u < G) {
                         const TileMeta2 m2 = s_meta2[gbase + k0 + u];
                         if (m2.cnt > 0) {
-                            V acc[VPL];  // accum = zero(Tiled), then += members in order (src/sparseupdate.jl:114-120)
+                            AccVec<T, VB> acc[VPL];  // accum = zero(Tiled), then += members in order (src/sparseupdate.jl:114-120)
 #pragma unroll
                             for (int p = 0; p < VPL; ++p)
 #pragma unroll
-                                for (int e = 0; e < V::NE; ++e) acc[p].e[e] = T(0) + v0[u][p].e[e];
+                                for (int e = 0; e < V::NE; ++e) acc[p].e[e] = acc_t<T>(0) + to_acc<T>(v0[u][p].e[e]);
                             if (m2.cnt > 1)  // a few duplicates (<= kShortMax members): the rest, strictly in order
                                 accumulate_members<T, VB, VPL, U>(acc, P.item[m2.slot], P.map, (int64_t)m2.start + 1,
                                                                   (int64_t)m2.start + m2.cnt, vi, G, gl, lane, gmask);
@@ -506,7 +523,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                                     V out;
 #pragma unroll
                                     for (int e = 0; e < V::NE; ++e)
-                                        out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[p].e[e], eta, m2.pad != 0);
+                                        out.e[e] = sgd_apply<T>(old[u][p].e[e], acc[p].e[e], eta, m2.pad != 0);
                                     st_plain<VB>(row + vi[p], &out);
                                 }
                             }
@@ -571,10 +588,16 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, (int32_t)md.table.pad};
     }
     __syncwarp();
-    const T eta = (T)P.eta;
+    const acc_t<T> eta = (acc_t<T>)P.eta;
 #pragma unroll 1
     for (int k0 = 0; k0 < G; k0 += UB) {
-        V old[UB][VPL], acc[UB][VPL];
+        // the first member's delta row is loaded straight into the accumulator registers when the arithmetic type
+        // is the storage type; the half types stage it and convert
+        constexpr bool kSame = sizeof(AccVec<T, VB>) == sizeof(V);
+        V old[UB][VPL];
+        AccVec<T, VB> acc[UB][VPL];
+        V first[kSame ? 1 : UB][kSame ? 1 : VPL];
+        (void)first;
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             if (s_meta2[gbase + k0 + u].cnt > 0) {
@@ -583,7 +606,8 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                 for (int p = 0; p < VPL; ++p) {
                     if (on[p]) {
                         ld_plain<VB>(&old[u][p], m.row + voff + p * G * VB);
-                        ld_row<VB>(&acc[u][p], m.d0 + voff + p * G * VB);
+                        if constexpr (kSame) ld_row<VB>(&acc[u][p], m.d0 + voff + p * G * VB);
+                        else ld_row<VB>(&first[u][p], m.d0 + voff + p * G * VB);
                     }
                 }
             }
@@ -595,7 +619,10 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
 #pragma unroll
                 for (int p = 0; p < VPL; ++p)
 #pragma unroll
-                    for (int e = 0; e < V::NE; ++e) acc[u][p].e[e] = T(0) + acc[u][p].e[e];  // accum = zero + first
+                    for (int e = 0; e < V::NE; ++e) {  // accum = zero + first
+                        if constexpr (kSame) acc[u][p].e[e] = acc_t<T>(0) + acc[u][p].e[e];
+                        else acc[u][p].e[e] = acc_t<T>(0) + to_acc<T>(first[u][p].e[e]);
+                    }
                 if (m2.cnt > 1) {  // up to kShortMax-1 more members, strictly in order
                     const UpdDesc& d = P.item[m2.slot];
                     for (int i = 1; i < m2.cnt; ++i) {
@@ -605,8 +632,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                             if (on[p]) {
                                 V v;
                                 ld_row<VB>(&v, r + p * G * VB);
-#pragma unroll
-                                for (int e = 0; e < V::NE; ++e) acc[u][p].e[e] = acc[u][p].e[e] + v.e[e];
+                                acc_add(acc[u][p], v);
                             }
                         }
                     }
@@ -617,7 +643,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                     if (on[p]) {
                         V out;
 #pragma unroll
-                        for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_epilogue<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
+                        for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_apply<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
                         st_plain<VB>(row + p * G * VB, &out);
                     }
                 }
@@ -642,7 +668,8 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
     const uint32_t n_tasks = P.counters->n_chunks;
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
-    const T eta = (T)P.eta;
+    const acc_t<T> eta = (acc_t<T>)P.eta;
+    constexpr int AS = (int)sizeof(AccVec<T, VB>) / VB;  // a partial row holds AccVecs
     const uint32_t groups_total = gridDim.x * (kUThreads / G);
     for (uint32_t i = blockIdx.x * (kUThreads / G) + threadIdx.x / G; i < n_tasks; i += groups_total) {
         const ChunkRec cr = P.chunks[i];
@@ -666,12 +693,12 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
             int vi[VPL];
 #pragma unroll
             for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
-            V old[VPL], acc[VPL];
+            V old[VPL];
+            AccVec<T, VB> acc[VPL];
 #pragma unroll
             for (int p = 0; p < VPL; ++p) {
                 if (medium) ld_plain<VB>(&old[p], row + vi[p]);
-#pragma unroll
-                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
+                acc_fill(acc[p], acc_t<T>(0));
             }
             accumulate_members<T, VB, VPL, U>(acc, d, P.map, a, b, vi, G, gl, lane, gmask);
 #pragma unroll
@@ -680,10 +707,10 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
                     if (medium) {
                         V out;
 #pragma unroll
-                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
+                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_apply<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
                         st_plain<VB>(row + vi[p], &out);
                     } else {
-                        st_plain<VB>(part + vi[p], &acc[p]);
+                        st_acc<T, VB>(part + (int64_t)vi[p] * AS, acc[p]);
                     }
                 }
             }
@@ -700,13 +727,15 @@ __global__ void __launch_bounds__(kUThreads)
 long_combine_kernel(const __grid_constant__ UpdParams P) {
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
     using V = Vec<T, VB>;
-    __shared__ __align__(16) char s_sum[kUThreads * VPL * VB];  // [group][G * VPL vectors]
+    using A = AccVec<T, VB>;
+    constexpr int AB = (int)sizeof(A);  // bytes of one accumulator vector (= VB except for the half types)
+    __shared__ __align__(16) char s_sum[kUThreads * VPL * AB];  // [group][G * VPL vectors]
     const int G = P.G, nvec = P.nvec;
     const int gl = threadIdx.x & (G - 1);
     const int grp = threadIdx.x / G, ngroups = kUThreads / G;
     const uint32_t n_long = P.counters->n_long;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
-    const T eta = (T)P.eta;
+    const acc_t<T> eta = (acc_t<T>)P.eta;
     for (uint32_t j = blockIdx.x; j < n_long; j += gridDim.x) {
         const LongRec lr = P.longs[j];
         const BucketRec rec = P.recs[lr.bucket];
@@ -720,43 +749,40 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
             int vi[VPL];
 #pragma unroll
             for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
-            V acc[VPL];
+            A acc[VPL];
 #pragma unroll
-            for (int p = 0; p < VPL; ++p)
-#pragma unroll
-                for (int k = 0; k < V::NE; ++k) acc[p].e[k] = T(0);
+            for (int p = 0; p < VPL; ++p) acc_fill(acc[p], acc_t<T>(0));
             for (uint32_t c0 = c_lo; c0 < c_hi; c0 += U) {
-                V v[U][VPL];
-#pragma unroll
-                for (int w = 0; w < U; ++w)
-                    if (c0 + w < c_hi)
-#pragma unroll
-                        for (int p = 0; p < VPL; ++p) ld_plain<VB>(&v[w][p], part + (int64_t)(c0 + w) * P.partial_pitch + vi[p]);
+                A v[U][VPL];
 #pragma unroll
                 for (int w = 0; w < U; ++w)
                     if (c0 + w < c_hi)
 #pragma unroll
                         for (int p = 0; p < VPL; ++p)
+                            ld_acc<T, VB>(v[w][p], part + (int64_t)(c0 + w) * P.partial_pitch + (int64_t)vi[p] * (AB / VB));
 #pragma unroll
-                            for (int k = 0; k < V::NE; ++k) acc[p].e[k] = acc[p].e[k] + v[w][p].e[k];
+                for (int w = 0; w < U; ++w)
+                    if (c0 + w < c_hi)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[w][p]);
             }
 #pragma unroll
-            for (int p = 0; p < VPL; ++p) *(V*)(s_sum + ((size_t)(grp * VPL + p) * G + gl) * VB) = acc[p];
+            for (int p = 0; p < VPL; ++p) *(A*)(s_sum + ((size_t)(grp * VPL + p) * G + gl) * AB) = acc[p];
             __syncthreads();
             if (grp == 0) {
 #pragma unroll
                 for (int p = 0; p < VPL; ++p) {
-                    V old, tot = *(const V*)(s_sum + ((size_t)p * G + gl) * VB);
+                    V old;
+                    A tot = *(const A*)(s_sum + ((size_t)p * G + gl) * AB);
                     if (pass0 + gl + p * G < nvec) ld_plain<VB>(&old, row + vi[p]);
                     for (int g2 = 1; g2 < used_groups; ++g2) {  // groups without chunks are skipped (no 0 + -0)
-                        const V v = *(const V*)(s_sum + ((size_t)(g2 * VPL + p) * G + gl) * VB);
-#pragma unroll
-                        for (int k = 0; k < V::NE; ++k) tot.e[k] = tot.e[k] + v.e[k];
+                        const A v = *(const A*)(s_sum + ((size_t)(g2 * VPL + p) * G + gl) * AB);
+                        acc_add(tot, v);
                     }
                     if (pass0 + gl + p * G < nvec) {
                         V out;
 #pragma unroll
-                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_epilogue<T>(old.e[k], tot.e[k], eta, d.table.pad != 0);
+                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_apply<T>(old.e[k], tot.e[k], eta, d.table.pad != 0);
                         st_plain<VB>(row + vi[p], &out);
                     }
                 }
@@ -778,6 +804,9 @@ static int pick_vb_update(const etb_update_item& it) {
             ((uintptr_t)it.delta % vb) == 0)
             return (int)vb;
     }
+    if (es == 2)  // half-precision rows must at least be 4-byte aligned
+        return (rowbytes % 4 == 0 && stride % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)it.table.base % 4) == 0 &&
+                ((uintptr_t)it.delta % 4) == 0) ? 4 : 0;
     return es == 8 ? 8 : 4;
 }
 
@@ -792,6 +821,10 @@ static UpdClass classify_update(const etb_update_item& it) {
     UpdClass c;
     c.elt = it.table.elt;
     c.vb = pick_vb_update(it);
+    if (c.vb == 0) {  // misaligned half-precision rows: rejected by the caller
+        c.nvec = c.G = c.vpl = 0;
+        return c;
+    }
     c.nvec = (int)((size_t)it.table.dim * elt_bytes(it.table.elt) / c.vb);
     c.G = std::min(32, pow2ceil(c.nvec));
     const int per_lane = (c.nvec + c.G - 1) / c.G;
@@ -819,7 +852,7 @@ static void launch_update_vpl(int which, int vpl, int grid, cudaStream_t s, cons
 
 template <typename T>
 static void launch_update_vb(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
-    if constexpr (sizeof(T) == 4) {
+    if constexpr (sizeof(T) <= 4) {
         if (c.vb == 4) return launch_update_vpl<T, 4>(which, c.vpl, grid, s, P);
     }
     if (c.vb == 8) return launch_update_vpl<T, 8>(which, c.vpl, grid, s, P);
@@ -830,6 +863,7 @@ template <typename T>
 static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     constexpr int UB = ETB_UPDATE_EXACT_UB;
     if (c.vb != 16 || c.nvec > c.G * c.vpl) return false;  // 16-byte vectors, row fits one pass
+    if (sizeof(T) == 2 && c.vpl > 1) return false;           // half types: 8 accumulators per vector, VPL > 1 would spill
 #define ETB_EXACT(VPLV, GV, UBV)                                                         \
     if (c.vpl == VPLV && c.G == GV) {                                                    \
         sgd_update_exact_kernel<T, VPLV, GV, (UBV)><<<grid, kUThreads, 0, s>>>(P);       \
@@ -843,10 +877,21 @@ static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, con
 
 static void launch_update(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain && ETB_UPDATE_USE_EXACT) {
-        if (c.elt == ETB_F32 ? launch_update_exact<float>(c, grid, s, P) : launch_update_exact<double>(c, grid, s, P)) return;
+        bool done;
+        switch (c.elt) {
+            case ETB_F32: done = launch_update_exact<float>(c, grid, s, P); break;
+            case ETB_F16: done = launch_update_exact<__half>(c, grid, s, P); break;
+            case ETB_BF16: done = launch_update_exact<__nv_bfloat16>(c, grid, s, P); break;
+            default: done = launch_update_exact<double>(c, grid, s, P); break;
+        }
+        if (done) return;
     }
-    if (c.elt == ETB_F32) launch_update_vb<float>(which, c, grid, s, P);
-    else launch_update_vb<double>(which, c, grid, s, P);
+    switch (c.elt) {
+        case ETB_F32: launch_update_vb<float>(which, c, grid, s, P); break;
+        case ETB_F16: launch_update_vb<__half>(which, c, grid, s, P); break;
+        case ETB_BF16: launch_update_vb<__nv_bfloat16>(which, c, grid, s, P); break;
+        default: launch_update_vb<double>(which, c, grid, s, P); break;
+    }
 }
 
 static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int32_t n_items,
@@ -954,11 +999,12 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         const etb_update_item& it = items[i];
         // update! on integer tables throws in the reference too (InexactError at
         // convert(eltype(table), opt.eta), src/sparseupdate.jl:173)
-        ETB_REQUIRE(it.table.elt == ETB_F32 || it.table.elt == ETB_F64,
-                    "etb_sgd_update: item %d: only Float32/Float64 tables can be updated", i);
+        ETB_REQUIRE(elt_is_float(it.table.elt), "etb_sgd_update: item %d: only floating-point tables can be updated", i);
         ETB_REQUIRE(it.batch == 0 || it.delta, "etb_sgd_update: item %d: null delta", i);
         ETB_REQUIRE(it.ld_delta >= it.table.dim, "etb_sgd_update: item %d: ld_delta < dim", i);
         cls[i] = classify_update(it);
+        if (cls[i].vb == 0)
+            return fail(ETB_ERR_UNSUPPORTED, "etb_sgd_update: item %d: half-precision rows must be 4-byte aligned (even dim, ld, ld_delta)", i);
     }
     ETB_REQUIRE(view->num_splits >= 0 && (view->num_splits == 0 || (view->this_split >= 1 && view->this_split <= view->num_splits)),
                 "etb_sgd_update: bad IndexerView split %d of %d", view->this_split, view->num_splits);
@@ -988,7 +1034,8 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
             const etb_update_item& it = items[i0 + n];
             UpdDesc& d = P.item[n];
             d.table = make_dev_table(it.table);
-            d.table.pad = ((flags | it.flags) & ETB_UPDATE_FMA) ? 1u : 0u;  // per-table epilogue
+            // per-table epilogue; the half types always take `row - eta*acc` in Float32 (see ETB_F16 in the header)
+            d.table.pad = (((flags | it.flags) & ETB_UPDATE_FMA) && elt_bytes(it.table.elt) >= 4) ? 1u : 0u;
             d.delta = (const char*)it.delta;
             d.ld_delta_bytes = it.ld_delta * (int64_t)elt_bytes(it.table.elt);
             ++n;
@@ -1086,7 +1133,7 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, voi
         while (vb > es && ((rows[r] * es) % vb || (row_off[r] * es) % vb || (uintptr_t)B.dense[r] % vb)) vb >>= 1;
     }
     while (vb > es && ((ld * es) % vb || (uintptr_t)strided % vb)) vb >>= 1;
-    if (vb < 4) vb = 4;
+    if (vb < 4) return fail(ETB_ERR_UNSUPPORTED, "etb_a2a: half-precision blocks must be 4-byte aligned (even row counts and offsets)");
     if (max_rows == 0) return ETB_OK;
     const int64_t total = max_rows * es / vb * batch_local;
     dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8), (unsigned)nranks);

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ETB_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libembtab_b200.so")
 
-F32, F64, I32, I64 = 0, 1, 2, 3
+F32, F64, I32, I64, F16, BF16 = 0, 1, 2, 3, 4, 5
 UPDATE_FMA, UPDATE_SPLIT_LONG = 1, 2
 
 

@@ -15,9 +15,31 @@ import torch
 from . import _lib
 
 _NP2T = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64,
-         np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
+         np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+         np.dtype(np.float16): torch.float16}
 _NP2ELT = {np.dtype(np.float32): _lib.F32, np.dtype(np.float64): _lib.F64,
-           np.dtype(np.int32): _lib.I32, np.dtype(np.int64): _lib.I64}
+           np.dtype(np.int32): _lib.I32, np.dtype(np.int64): _lib.I64,
+           np.dtype(np.float16): _lib.F16}
+try:   # numpy has no bfloat16 of its own; ml_dtypes provides one (round-to-nearest-even conversions)
+    import ml_dtypes
+    bfloat16 = np.dtype(ml_dtypes.bfloat16)
+    _NP2T[bfloat16] = torch.bfloat16
+    _NP2ELT[bfloat16] = _lib.BF16
+except ImportError:   # bf16 tables then need the C ABI directly
+    bfloat16 = None
+
+
+def _np_to_torch(flat: np.ndarray) -> torch.Tensor:
+    """torch.from_numpy, also for bfloat16 (which torch's numpy bridge does not know)"""
+    if bfloat16 is not None and flat.dtype == bfloat16:
+        return torch.from_numpy(flat.view(np.int16)).view(torch.bfloat16)
+    return torch.from_numpy(flat)
+
+
+def _torch_to_np(t: torch.Tensor) -> np.ndarray:
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).numpy().view(bfloat16)
+    return t.numpy()
 
 
 def current_stream_ptr() -> int:
@@ -61,7 +83,7 @@ class DeviceArray:
         require_cuda()
         a = np.asarray(a, dtype=dtype)
         flat = np.ascontiguousarray(a.reshape(-1, order="F"))
-        buf = torch.from_numpy(flat).to(device or "cuda")
+        buf = _np_to_torch(flat).to(device or "cuda")
         return DeviceArray(buf, a.shape, dtype=a.dtype)
 
     @staticmethod
@@ -141,12 +163,12 @@ class DeviceArray:
         """Download as a Fortran-ordered numpy array of the Julia shape."""
         if self.ndim == 2 and not self.is_dense:
             span = (self.shape[1] - 1) * self.ld + self.shape[0]
-            flat = self.buf[self.offset:self.offset + span].cpu().numpy()
+            flat = _torch_to_np(self.buf[self.offset:self.offset + span].cpu())
             full = np.lib.stride_tricks.as_strided(
                 flat, shape=self.shape, strides=(self.itemsize, self.ld * self.itemsize))
             return np.asfortranarray(full)
         n = int(np.prod(self.shape)) if self.shape else 1
-        flat = self.buf[self.offset:self.offset + n].cpu().numpy()
+        flat = _torch_to_np(self.buf[self.offset:self.offset + n].cpu())
         return flat.reshape(self.shape, order="F")
 
     def copy_from(self, a) -> "DeviceArray":
@@ -155,11 +177,11 @@ class DeviceArray:
         if self.ndim == 2 and not self.is_dense:
             for j in range(self.shape[1]):
                 s = self.offset + j * self.ld
-                self.buf[s:s + self.shape[0]].copy_(torch.from_numpy(np.ascontiguousarray(a[:, j])))
+                self.buf[s:s + self.shape[0]].copy_(_np_to_torch(np.ascontiguousarray(a[:, j])))
             return self
         n = int(np.prod(self.shape)) if self.shape else 1
         self.buf[self.offset:self.offset + n].copy_(
-            torch.from_numpy(np.ascontiguousarray(a.reshape(-1, order="F"))))
+            _np_to_torch(np.ascontiguousarray(a.reshape(-1, order="F"))))
         return self
 
     def upload(self, host: np.ndarray) -> "DeviceArray":
@@ -229,7 +251,7 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
     """A page-locked host array (Fortran order, Julia shape) for asynchronous upload/download."""
     shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
     t = torch.empty(int(np.prod(shape)), dtype=_NP2T[np.dtype(dtype)], pin_memory=True)
-    a = t.numpy().reshape(shape, order="F")
+    a = _torch_to_np(t).reshape(shape, order="F")
     _PINNED_KEEPALIVE[a.ctypes.data] = t
     return a
 

@@ -59,7 +59,14 @@ typedef enum etb_dtype {
     ETB_F32 = 0,
     ETB_F64 = 1,
     ETB_I32 = 2,
-    ETB_I64 = 3
+    ETB_I64 = 3,
+    /* Extension (no reference counterpart -- the reference's tables are Float32/Float64/integer):
+     * half-precision storage with Float32 arithmetic.  Pooled sums and SGD updates convert each element to
+     * Float32, accumulate in the reference's order, and round to nearest-even ONCE when the result is stored
+     * (output / cotangent have the table's element type).  The update epilogue is `row - eta*acc` in Float32
+     * (ETB_UPDATE_FMA is ignored).  dim and every leading dimension must be even (4-byte aligned rows). */
+    ETB_F16 = 4,
+    ETB_BF16 = 5
 } etb_dtype;
 
 /* flags of etb_sgd_update* */

@@ -298,3 +298,37 @@ def uncompress(delta, I, dstcols):
 
 def force_portable(on: bool):
     lib().etbo_force_portable(C.c_int(int(on)))
+
+
+# ------------------------------------------------------------------ half-precision extension
+# ETB_F16 / ETB_BF16 tables have NO reference counterpart: the reference's tables are
+# Float32/Float64/integer.  PARITY UNPINNED for this extension -- these functions DEFINE its semantics
+# (include/embtab_b200.h, ETB_F16): every element is converted to Float32 (exact), sums run in Float32 in the
+# reference's order (pooled: accumulator = first row, then bag order; update: 0 + members in occurrence order),
+# the update epilogue is `row - eta*acc` in Float32 with separate roundings, and the result is rounded to the
+# storage type once (nearest-even).  numpy's float32 ufuncs round each operation separately, like the kernels.
+def lookup_lowp(data, I):
+    data = np.asarray(data)
+    I = np.asarray(I, dtype=np.int64)
+    if I.ndim == 1:
+        return np.asfortranarray(data[:, I - 1])
+    acc = data[:, I[0] - 1].astype(np.float32)
+    for k in range(1, I.shape[0]):
+        acc = acc + data[:, I[k] - 1].astype(np.float32)
+    return np.asfortranarray(acc.astype(data.dtype))
+
+
+def update_lowp(data, delta, I, eta):
+    """in place on `data` (featuresize x nrows, float16 / ml_dtypes.bfloat16)"""
+    I = np.asarray(I, dtype=np.int64)
+    bag = I.shape[0] if I.ndim == 2 else 1
+    flat = I.reshape(-1, order="F")
+    eta32 = np.float32(eta)
+    acc = {}
+    for p, r in enumerate(flat.tolist()):
+        d = np.asarray(delta[:, p // bag]).astype(np.float32)
+        acc[r] = (acc[r] + d) if r in acc else (np.float32(0) + d)
+    for r, a in acc.items():
+        row = data[:, r - 1].astype(np.float32)
+        data[:, r - 1] = (row - eta32 * a).astype(data.dtype)
+    return data

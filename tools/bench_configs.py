@@ -246,11 +246,46 @@ def config_update_sweep(fh):
         torch.cuda.empty_cache()
 
 
+def config_lowp(fh):
+    """C2's shape with half-precision tables (ETB_F16 / ETB_BF16, Float32 arithmetic) beside Float32: the forward
+    and the update kernels move half the bytes per row."""
+    nrows, nt, bag, batch, dim = 1_000_000, 26, 32, 16384, 128
+    rng = np.random.default_rng(0xE7AB1E + 7)
+    I_host = rng.integers(1, nrows + 1, (bag, batch, nt))
+    u = sum(int(np.unique(I_host[:, :, t]).size) for t in range(nt))
+    I = E.DeviceArray.from_numpy(I_host)
+    Is = list(E.colwrap(I))
+    for name, tdt, ndt in (("f32", torch.float32, np.float32), ("f16", torch.float16, np.float16), ("bf16", torch.bfloat16, E.bfloat16)):
+        es = np.dtype(ndt).itemsize
+        gen = torch.Generator(device="cuda").manual_seed(1)
+        tables = []
+        for _ in range(nt):
+            buf = torch.rand(dim * nrows, device="cuda", dtype=torch.float32, generator=gen).to(tdt)
+            tables.append(E.SimpleEmbedding(E.DeviceArray(buf, (dim, nrows)), E.Static(dim)))
+        out = E.DeviceArray.empty((128 + nt * dim, batch), ndt)
+        strategy = E.PreallocationStrategy(128)
+        t_f = timeit(lambda: E.maplookup_(strategy, out, tables, I), iters=10, warmup=3)
+        delta = E.DeviceArray(torch.randn(nt * dim * batch, device="cuda").to(tdt), (nt * dim, batch))
+        grads = [E.SparseEmbeddingUpdate(E.Static(dim), delta.rows(k * dim, (k + 1) * dim), i) for k, i in enumerate(Is)]
+        indexer = E.Indexer()
+        E.index_(indexer, tables, grads)
+        t_k = timeit(lambda: E.sparseupdate._apply(tables, grads, indexer, 0.01), iters=10, warmup=3)
+        t_i = timeit(lambda: E.index_(indexer, tables, grads), iters=10, warmup=3)
+        fb = nt * batch * (bag * (8 + dim * es) + dim * es)
+        ub = nt * batch * dim * es + 2 * u * dim * es + nt * batch * bag * 4
+        step = t_f + t_i + t_k
+        emit({"config": "c2-lowp", "dtype": name, "fwd_ms": t_f, "index_ms": t_i, "update_ms": t_k, "step_ms_back_to_back": step,
+              "lookups_per_sec": nt * batch * bag / (step * 1e-3), "fwd_gbs": fb / t_f / 1e6, "fwd_frac_of_measured_peak": fb / t_f / 1e6 / PEAK,
+              "update_gbs": ub / t_k / 1e6, "update_frac_of_measured_peak": ub / t_k / 1e6 / PEAK}, fh)
+        del tables, delta, grads, indexer, out
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4local", "c5", "c5quick", "update"])
+    ap.add_argument("--config", required=True, choices=["c1", "c3", "c4local", "c5", "c5quick", "update", "lowp"])
     ap.add_argument("--out")
     a = ap.parse_args()
     E._lib.check(E.lib().etb_init(0))
     fh = open(a.out, "a") if a.out else None
-    {"c1": config_c1, "c3": config_c3, "c4local": config_c4local, "update": config_update_sweep, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)
+    {"lowp": config_lowp, "c1": config_c1, "c3": config_c3, "c4local": config_c4local, "update": config_update_sweep, "c5": config_c5, "c5quick": lambda f: config_c5(f, True)}[a.config](fh)

@@ -93,6 +93,8 @@ Every number comes from `gpurun` runs on B200s of this pool.  The `.ncu-rep` fil
 | `r1_sass_excerpts.txt` | `cuobjdump -sass` of the two hot kernels: the independent `LDG.E.128` of a batch issued back to back before the ordered `FADD` / `FFMA` chain |
 | `r1_ubench_random_rmw_ceiling.json` | `tools/ubench_rmw.cu`: what HBM delivers for random 512-byte RMW / reads |
 | `r1_c1_*.jsonl`, `r1_c3_*.jsonl`, `r1_c4_*.jsonl`, `r1_c5_sweep.jsonl` | `tools/bench_configs.py`: the other BASELINE configs |
+| `r1_c2_lowp.jsonl` | `tools/bench_configs.py --config lowp`: C2's shape with Float16 / BFloat16 tables (extension) beside Float32 |
+| `r1_zero_copy_probe.jsonl` | `tools/zero_copy_probe.py`: kernels reading / writing pinned host buffers directly |
 
 compute-sanitizer is closed on this pool (`gpurun` refuses it); `tools/sanitize_smoke.py` (a pass over every kernel
 family with odd shapes) runs clean without it, and bounds are covered by canary checks in the parity tests.
