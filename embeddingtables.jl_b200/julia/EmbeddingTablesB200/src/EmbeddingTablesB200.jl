@@ -56,6 +56,8 @@ etb_elt(::Type{Float32}) = Int32(0)
 etb_elt(::Type{Float64}) = Int32(1)
 etb_elt(::Type{Int32}) = Int32(2)
 etb_elt(::Type{Int64}) = Int32(3)
+etb_elt(::Type{Float16}) = Int32(4)   # extension: half-precision storage, Float32 arithmetic (ETB_F16)
+# BFloat16s.BFloat16 maps to Int32(5) (ETB_BF16); add `etb_elt(::Type{BFloat16}) = Int32(5)` where BFloat16s is loaded
 
 function check(status::Integer)
     status == 0 && return nothing
