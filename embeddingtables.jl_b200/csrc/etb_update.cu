@@ -321,7 +321,12 @@ struct UpdParams {
     int32_t G, nvec;
     int32_t fma, split_long;
     int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:564-572
+    // row-wise Adagrad only (OPT == kOptAdagrad): per-item state vectors (one acc_t element per table row)
+    double eps;
+    char* state[kUMaxItems];
 };
+
+enum { kOptSgd = 0, kOptAdagrad = 1 };
 
 template <typename T>
 __device__ __forceinline__ T sgd_epilogue(T row, T acc, T eta, bool fma);
@@ -352,6 +357,48 @@ template <typename T, int VB>
 __device__ __forceinline__ void st_acc(char* p, const AccVec<T, VB>& a) {
 #pragma unroll
     for (int k = 0; k < (int)sizeof(AccVec<T, VB>) / VB; ++k) st_plain<VB>(p + k * VB, (const char*)&a + k * VB);
+}
+
+// correctly rounded, never contracted (the parity tests repeat these operations one by one on the CPU)
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+
+// Row-wise Adagrad (extension; the reference has Descent only, src/sparseupdate.jl:160-189).
+// g = the bucket's summed cotangent (same order as the SGD path).  One state element per table row:
+//     h = state[row] + (sum_d g_d^2) / dim;  state[row] = h;  row -= (eta / (sqrt(h) + eps)) * g
+// The sum of squares has a fixed order: every lane adds the squares of its own elements (vector p ascending,
+// element ascending), then the G lanes of the group are combined by an XOR butterfly (offsets G/2 ... 1); a + b is
+// commutative, so every lane ends with the same bits.  Lanes past the row (`on[p]` false) contribute nothing.
+// Called by all lanes of the group together; the row must fit one pass (nvec <= G * VPL, checked by the host).
+template <typename T, int VB, int VPL>
+__device__ __forceinline__ void adagrad_apply(Vec<T, VB> (&out)[VPL], const Vec<T, VB> (&old)[VPL],
+                                              const AccVec<T, VB> (&g)[VPL], const bool (&on)[VPL], acc_t<T>* state,
+                                              acc_t<T> eta, acc_t<T> eps, int dim, int G, int gl, unsigned gmask) {
+    using A = acc_t<T>;
+    A s = A(0);
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+        if (on[p])
+#pragma unroll
+            for (int e = 0; e < Vec<T, VB>::NE; ++e) s = add_rn(s, mul_rn(g[p].e[e], g[p].e[e]));
+    for (int off = G >> 1; off > 0; off >>= 1) s = add_rn(s, __shfl_xor_sync(gmask, s, off));
+    const A h = add_rn(*state, div_rn(s, (A)dim));
+    __syncwarp(gmask);  // every lane has read the old state before lane 0 replaces it
+    if (gl == 0) *state = h;
+    const A scale = div_rn(eta, add_rn(sqrt_rn(h), eps));
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+        for (int e = 0; e < Vec<T, VB>::NE; ++e)
+            out[p].e[e] = from_acc<T>(sub_rn(to_acc<T>(old[p].e[e]), mul_rn(scale, g[p].e[e])));
 }
 
 __device__ __forceinline__ unsigned group_mask(int G, int lane) {
@@ -426,7 +473,7 @@ struct alignas(16) TileMeta2 {
     int32_t pad;
 };
 
-template <typename T, int VB, int VPL>
+template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads, ETB_UPDATE_MIN_BLOCKS)
 sgd_update_kernel(const __grid_constant__ UpdParams P) {
     constexpr int UB = (ETB_UPDATE_UB / VPL) > 1 ? (ETB_UPDATE_UB / VPL) : 1;  // buckets in flight per group
@@ -479,7 +526,9 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
         m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
         s_meta[wbase + r * 32 + lane] = m;
-        s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0, (int32_t)md.table.pad};
+        // pad: the SGD epilogue's FMA flag, or (Adagrad) the row number for the state vector
+        s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0,
+                                                   OPT == kOptSgd ? (int32_t)md.table.pad : (int32_t)(key & row_mask)};
     }
     __syncwarp();
 
@@ -517,15 +566,27 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
                                 accumulate_members<T, VB, VPL, U>(acc, P.item[m2.slot], P.map, (int64_t)m2.start + 1,
                                                                   (int64_t)m2.start + m2.cnt, vi, G, gl, lane, gmask);
                             char* row = const_cast<char*>(s_meta[gbase + k0 + u].row);
+                            if constexpr (OPT == kOptSgd) {
 #pragma unroll
-                            for (int p = 0; p < VPL; ++p) {
-                                if (pass0 + gl + p * G < nvec) {
-                                    V out;
+                                for (int p = 0; p < VPL; ++p) {
+                                    if (pass0 + gl + p * G < nvec) {
+                                        V out;
 #pragma unroll
-                                    for (int e = 0; e < V::NE; ++e)
-                                        out.e[e] = sgd_apply<T>(old[u][p].e[e], acc[p].e[e], eta, m2.pad != 0);
-                                    st_plain<VB>(row + vi[p], &out);
+                                        for (int e = 0; e < V::NE; ++e)
+                                            out.e[e] = sgd_apply<T>(old[u][p].e[e], acc[p].e[e], eta, m2.pad != 0);
+                                        st_plain<VB>(row + vi[p], &out);
+                                    }
                                 }
+                            } else {
+                                bool on[VPL];
+#pragma unroll
+                                for (int p = 0; p < VPL; ++p) on[p] = gl + p * G < nvec;
+                                V out[VPL];
+                                adagrad_apply<T, VB, VPL>(out, old[u], acc, on, (acc_t<T>*)P.state[m2.slot] + m2.pad, eta,
+                                                          (acc_t<T>)P.eps, nvec * V::NE, G, gl, gmask);
+#pragma unroll
+                                for (int p = 0; p < VPL; ++p)
+                                    if (on[p]) st_plain<VB>(row + vi[p], &out[p]);
                             }
                         }
                     }
@@ -542,7 +603,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
 // the generic one -- which is what the random 512-byte read-modify-write pattern wants: the HBM
 // ceiling (6.5 TB/s, tools/ubench_rmw.cu) is reached with only 4 rows in flight per warp but needs
 // ~all warp slots filled.
-template <typename T, int VPL, int G, int UB>
+template <typename T, int VPL, int G, int UB, int OPT>
 __global__ void __launch_bounds__(kUThreads, ETB_UPDATE_EXACT_MIN_BLOCKS)
 sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
     constexpr int VB = 16;
@@ -585,7 +646,8 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
         m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
         s_meta[threadIdx.x] = m;
-        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0, (int32_t)md.table.pad};
+        s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0,
+                                         OPT == kOptSgd ? (int32_t)md.table.pad : (int32_t)(key & row_mask)};
     }
     __syncwarp();
     const acc_t<T> eta = (acc_t<T>)P.eta;
@@ -638,14 +700,23 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                     }
                 }
                 char* row = const_cast<char*>(s_meta[gbase + k0 + u].row) + voff;
+                if constexpr (OPT == kOptSgd) {
 #pragma unroll
-                for (int p = 0; p < VPL; ++p) {
-                    if (on[p]) {
-                        V out;
+                    for (int p = 0; p < VPL; ++p) {
+                        if (on[p]) {
+                            V out;
 #pragma unroll
-                        for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_apply<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
-                        st_plain<VB>(row + p * G * VB, &out);
+                            for (int e = 0; e < V::NE; ++e) out.e[e] = sgd_apply<T>(old[u][p].e[e], acc[u][p].e[e], eta, m2.pad != 0);
+                            st_plain<VB>(row + p * G * VB, &out);
+                        }
                     }
+                } else {
+                    V out[VPL];
+                    adagrad_apply<T, VB, VPL>(out, old[u], acc[u], on, (acc_t<T>*)P.state[m2.slot] + m2.pad, eta,
+                                              (acc_t<T>)P.eps, P.nvec * V::NE, G, lane & (G - 1), group_mask(G, lane));
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p)
+                        if (on[p]) st_plain<VB>(row + p * G * VB, &out[p]);
                 }
             }
         }
@@ -656,7 +727,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
 // strictly in occurrence order from zero, 8 rows in flight -- so they share one worklist and one
 // launch (they overlap instead of running back to back).  A medium task finishes its table row; a
 // chunk task writes its partial row.
-template <typename T, int VB, int VPL>
+template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads, 2)  // up to 128 registers: a spill of loaded rows serialises the loads
 bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
@@ -701,6 +772,19 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
                 acc_fill(acc[p], acc_t<T>(0));
             }
             accumulate_members<T, VB, VPL, U>(acc, d, P.map, a, b, vi, G, gl, lane, gmask);
+            if (OPT == kOptAdagrad && medium) {  // single pass (host-checked); the whole group is here together
+                bool on[VPL];
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) on[p] = gl + p * G < nvec;
+                V out[VPL];
+                const int slot = (int)(rec.key >> P.row_bits) - P.slot0;
+                adagrad_apply<T, VB, VPL>(out, old, acc, on, (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask), eta,
+                                          (acc_t<T>)P.eps, nvec * V::NE, G, gl, gmask);
+#pragma unroll
+                for (int p = 0; p < VPL; ++p)
+                    if (on[p]) st_plain<VB>(row + vi[p], &out[p]);
+                continue;
+            }
 #pragma unroll
             for (int p = 0; p < VPL; ++p) {
                 if (pass0 + gl + p * G < nvec) {
@@ -722,7 +806,7 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
 // the bucket's partial rows in chunk order (8 in flight); the group sums are then added in group order
 // through shared memory and the epilogue is applied.  The split depends only on the chunk count:
 // deterministic.
-template <typename T, int VB, int VPL>
+template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads)
 long_combine_kernel(const __grid_constant__ UpdParams P) {
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
@@ -770,21 +854,37 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
             for (int p = 0; p < VPL; ++p) *(A*)(s_sum + ((size_t)(grp * VPL + p) * G + gl) * AB) = acc[p];
             __syncthreads();
             if (grp == 0) {
+                V old[VPL];
+                A tot[VPL];
+                bool on[VPL];
 #pragma unroll
                 for (int p = 0; p < VPL; ++p) {
-                    V old;
-                    A tot = *(const A*)(s_sum + ((size_t)p * G + gl) * AB);
-                    if (pass0 + gl + p * G < nvec) ld_plain<VB>(&old, row + vi[p]);
+                    tot[p] = *(const A*)(s_sum + ((size_t)p * G + gl) * AB);
+                    on[p] = pass0 + gl + p * G < nvec;
+                    if (on[p]) ld_plain<VB>(&old[p], row + vi[p]);
                     for (int g2 = 1; g2 < used_groups; ++g2) {  // groups without chunks are skipped (no 0 + -0)
                         const A v = *(const A*)(s_sum + ((size_t)(g2 * VPL + p) * G + gl) * AB);
-                        acc_add(tot, v);
+                        acc_add(tot[p], v);
                     }
-                    if (pass0 + gl + p * G < nvec) {
-                        V out;
+                }
+                if constexpr (OPT == kOptSgd) {
 #pragma unroll
-                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_apply<T>(old.e[k], tot.e[k], eta, d.table.pad != 0);
-                        st_plain<VB>(row + vi[p], &out);
+                    for (int p = 0; p < VPL; ++p) {
+                        if (on[p]) {
+                            V out;
+#pragma unroll
+                            for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_apply<T>(old[p].e[k], tot[p].e[k], eta, d.table.pad != 0);
+                            st_plain<VB>(row + vi[p], &out);
+                        }
                     }
+                } else {  // single pass (host-checked); group 0 = the first G lanes of warp 0
+                    V out[VPL];
+                    const int slot = (int)(rec.key >> P.row_bits) - P.slot0;
+                    adagrad_apply<T, VB, VPL>(out, old, tot, on, (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask), eta,
+                                              (acc_t<T>)P.eps, nvec * V::NE, G, gl, group_mask(G, threadIdx.x & 31));
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p)
+                        if (on[p]) st_plain<VB>(row + vi[p], &out[p]);
                 }
             }
             __syncthreads();
@@ -834,39 +934,39 @@ static UpdClass classify_update(const etb_update_item& it) {
 
 enum { kKernelMain = 0, kKernelTasks = 1, kKernelCombine = 2 };
 
-template <typename T, int VB, int VPL>
+template <typename T, int VB, int VPL, int OPT>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
-    if (which == kKernelMain) sgd_update_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
-    else if (which == kKernelTasks) bucket_tasks_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
-    else long_combine_kernel<T, VB, VPL><<<grid, kUThreads, 0, s>>>(P);
+    if (which == kKernelMain) sgd_update_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
+    else if (which == kKernelTasks) bucket_tasks_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
+    else long_combine_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
 }
 
-template <typename T, int VB>
+template <typename T, int VB, int OPT>
 static void launch_update_vpl(int which, int vpl, int grid, cudaStream_t s, const UpdParams& P) {
     switch (vpl) {
-        case 1: launch_update_one<T, VB, 1>(which, grid, s, P); break;
-        case 2: launch_update_one<T, VB, 2>(which, grid, s, P); break;
-        default: launch_update_one<T, VB, 4>(which, grid, s, P); break;
+        case 1: launch_update_one<T, VB, 1, OPT>(which, grid, s, P); break;
+        case 2: launch_update_one<T, VB, 2, OPT>(which, grid, s, P); break;
+        default: launch_update_one<T, VB, 4, OPT>(which, grid, s, P); break;
     }
 }
 
-template <typename T>
+template <typename T, int OPT>
 static void launch_update_vb(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     if constexpr (sizeof(T) <= 4) {
-        if (c.vb == 4) return launch_update_vpl<T, 4>(which, c.vpl, grid, s, P);
+        if (c.vb == 4) return launch_update_vpl<T, 4, OPT>(which, c.vpl, grid, s, P);
     }
-    if (c.vb == 8) return launch_update_vpl<T, 8>(which, c.vpl, grid, s, P);
-    return launch_update_vpl<T, 16>(which, c.vpl, grid, s, P);
+    if (c.vb == 8) return launch_update_vpl<T, 8, OPT>(which, c.vpl, grid, s, P);
+    return launch_update_vpl<T, 16, OPT>(which, c.vpl, grid, s, P);
 }
 
-template <typename T>
+template <typename T, int OPT>
 static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     constexpr int UB = ETB_UPDATE_EXACT_UB;
     if (c.vb != 16 || c.nvec > c.G * c.vpl) return false;  // 16-byte vectors, row fits one pass
     if (sizeof(T) == 2 && c.vpl > 1) return false;           // half types: 8 accumulators per vector, VPL > 1 would spill
 #define ETB_EXACT(VPLV, GV, UBV)                                                         \
     if (c.vpl == VPLV && c.G == GV) {                                                    \
-        sgd_update_exact_kernel<T, VPLV, GV, (UBV)><<<grid, kUThreads, 0, s>>>(P);       \
+        sgd_update_exact_kernel<T, VPLV, GV, (UBV), OPT><<<grid, kUThreads, 0, s>>>(P);  \
         return true;                                                                     \
     }
     ETB_EXACT(1, 32, UB) ETB_EXACT(1, 16, UB) ETB_EXACT(1, 8, UB) ETB_EXACT(1, 4, UB < 4 ? UB : 4)
@@ -875,23 +975,29 @@ static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, con
     return false;
 }
 
-static void launch_update(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+template <int OPT>
+static void launch_update_opt(int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain && ETB_UPDATE_USE_EXACT) {
         bool done;
         switch (c.elt) {
-            case ETB_F32: done = launch_update_exact<float>(c, grid, s, P); break;
-            case ETB_F16: done = launch_update_exact<__half>(c, grid, s, P); break;
-            case ETB_BF16: done = launch_update_exact<__nv_bfloat16>(c, grid, s, P); break;
-            default: done = launch_update_exact<double>(c, grid, s, P); break;
+            case ETB_F32: done = launch_update_exact<float, OPT>(c, grid, s, P); break;
+            case ETB_F16: done = launch_update_exact<__half, OPT>(c, grid, s, P); break;
+            case ETB_BF16: done = launch_update_exact<__nv_bfloat16, OPT>(c, grid, s, P); break;
+            default: done = launch_update_exact<double, OPT>(c, grid, s, P); break;
         }
         if (done) return;
     }
     switch (c.elt) {
-        case ETB_F32: launch_update_vb<float>(which, c, grid, s, P); break;
-        case ETB_F16: launch_update_vb<__half>(which, c, grid, s, P); break;
-        case ETB_BF16: launch_update_vb<__nv_bfloat16>(which, c, grid, s, P); break;
-        default: launch_update_vb<double>(which, c, grid, s, P); break;
+        case ETB_F32: launch_update_vb<float, OPT>(which, c, grid, s, P); break;
+        case ETB_F16: launch_update_vb<__half, OPT>(which, c, grid, s, P); break;
+        case ETB_BF16: launch_update_vb<__nv_bfloat16, OPT>(which, c, grid, s, P); break;
+        default: launch_update_vb<double, OPT>(which, c, grid, s, P); break;
     }
+}
+
+static void launch_update(int opt, int which, const UpdClass& c, int grid, cudaStream_t s, const UpdParams& P) {
+    if (opt == kOptAdagrad) launch_update_opt<kOptAdagrad>(which, c, grid, s, P);
+    else launch_update_opt<kOptSgd>(which, c, grid, s, P);
 }
 
 static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int32_t n_items,
@@ -987,7 +1093,8 @@ static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* item
 }
 
 static int32_t update_impl(const etb_index_view* view, const etb_update_item* items, int32_t n_items, double eta,
-                           int32_t flags, cudaStream_t stream) {
+                           int32_t flags, cudaStream_t stream, int opt = kOptSgd, void* const* states = nullptr,
+                           double eps = 0.0) {
     ETB_REQUIRE(view, "etb_sgd_update: null index view");
     ETB_REQUIRE(n_items >= 0 && (n_items == 0 || items), "etb_sgd_update: bad items");
     if (n_items == 0 || view->n_total == 0) return ETB_OK;
@@ -1005,6 +1112,13 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         cls[i] = classify_update(it);
         if (cls[i].vb == 0)
             return fail(ETB_ERR_UNSUPPORTED, "etb_sgd_update: item %d: half-precision rows must be 4-byte aligned (even dim, ld, ld_delta)", i);
+        if (opt == kOptAdagrad) {
+            ETB_REQUIRE(states && states[i], "etb_adagrad_update: item %d: null state vector", i);
+            ETB_REQUIRE(it.table.nrows <= 0x7fffffffll, "etb_adagrad_update: item %d: more than 2^31 rows", i);
+            if (cls[i].nvec > cls[i].G * cls[i].vpl)
+                return fail(ETB_ERR_UNSUPPORTED, "etb_adagrad_update: item %d: rows of more than %d vectors of %d bytes are not supported",
+                            i, cls[i].G * cls[i].vpl, cls[i].vb);
+        }
     }
     ETB_REQUIRE(view->num_splits >= 0 && (view->num_splits == 0 || (view->this_split >= 1 && view->this_split <= view->num_splits)),
                 "etb_sgd_update: bad IndexerView split %d of %d", view->this_split, view->num_splits);
@@ -1020,6 +1134,7 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
     P.partial_pitch = (int64_t)L.partial_pitch;
     P.n_total = view->n_total;
     P.eta = eta;
+    P.eps = eps;
     P.row_bits = view->row_bits;
     P.fma = (flags & ETB_UPDATE_FMA) ? 1 : 0;
     P.split_long = (flags & ETB_UPDATE_SPLIT_LONG) ? 1 : 0;
@@ -1038,6 +1153,7 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
             d.table.pad = (((flags | it.flags) & ETB_UPDATE_FMA) && elt_bytes(it.table.elt) >= 4) ? 1u : 0u;
             d.delta = (const char*)it.delta;
             d.ld_delta_bytes = it.ld_delta * (int64_t)elt_bytes(it.table.elt);
+            P.state[n] = opt == kOptAdagrad ? (char*)states[i0 + n] : nullptr;
             ++n;
         }
         P.slot0 = i0;
@@ -1047,19 +1163,19 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
         const int64_t buckets_per_block = (kUThreads / 32) * 32 * ETB_UPDATE_RPL;  // one tile per warp
         const int grid = (int)((view->n_total + buckets_per_block - 1) / buckets_per_block);
-        launch_update(kKernelMain, c, grid, stream, P);
+        launch_update(opt, kKernelMain, c, grid, stream, P);
         ETB_LAUNCHED();
         const int64_t per_block = kUThreads / c.G;
         if (view->n_total > kShortMax) {  // medium buckets + long-bucket chunks: one task kernel
             const int64_t max_tasks = view->n_total / (kShortMax + 1) + 1;
             const int gridT = (int)std::min<int64_t>((max_tasks + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
-            launch_update(kKernelTasks, c, gridT, stream, P);
+            launch_update(opt, kKernelTasks, c, gridT, stream, P);
             ETB_LAUNCHED();
         }
         if (P.split_long && view->n_total > kLongThreshold) {
             const int64_t max_long = view->n_total / kLongThreshold + 1;
             const int gridB = (int)std::min<int64_t>(max_long, (int64_t)kNumSMs * 4);  // one CTA per long bucket
-            launch_update(kKernelCombine, c, gridB, stream, P);
+            launch_update(opt, kKernelCombine, c, gridB, stream, P);
             ETB_LAUNCHED();
         }
         i0 += n;
@@ -1171,6 +1287,14 @@ int32_t etb_sgd_update(const etb_index_view* view_host, const etb_update_item* i
                        int32_t flags, void* stream) {
     launch_counter() = 0;
     return update_impl(view_host, items_host, n_items, eta, flags, (cudaStream_t)stream);
+}
+
+int32_t etb_adagrad_update(const etb_index_view* view_host, const etb_update_item* items_host, void* const* states_host,
+                           int32_t n_items, double eta, double eps, int32_t flags, void* stream) {
+    launch_counter() = 0;
+    ETB_REQUIRE(eps >= 0.0, "etb_adagrad_update: negative eps");
+    return update_impl(view_host, items_host, n_items, eta, flags & ~ETB_UPDATE_FMA, (cudaStream_t)stream, kOptAdagrad,
+                       states_host, eps);
 }
 
 int32_t etb_index_and_update(void* workspace, size_t workspace_bytes, const etb_update_item* items_host,

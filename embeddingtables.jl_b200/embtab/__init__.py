@@ -9,7 +9,7 @@ from .darray import DeviceArray, as_device, as_device_indices, bfloat16, pinned_
 from .graph import capture
 from .lookup import (AbstractExecutionStrategy, ColumnWrap, DefaultStrategy, PreallocationStrategy,
                      SimpleParallelStrategy, colwrap, destination, lookup, lookup_, maplookup, maplookup_)
-from .sparseupdate import (AbstractIndexer, DenseIndexer, Descent, Indexer, IndexerView, Slicer,
+from .sparseupdate import (AbstractIndexer, Adagrad, DenseIndexer, Descent, Indexer, IndexerView, Slicer,
                            SparseEmbeddingUpdate, SparseIndexer, ensemble_update, index_, prefetch_index, pullback, rrule,
                            set_update_order,
                            uncompress, update_, update_table_)

@@ -74,6 +74,8 @@ _SIGS = {
                    C.c_void_p], C.c_int32),
     "etb_sgd_update": ([C.POINTER(IndexView), C.POINTER(UpdateItem), C.c_int32, C.c_double, C.c_int32,
                         C.c_void_p], C.c_int32),
+    "etb_adagrad_update": ([C.POINTER(IndexView), C.POINTER(UpdateItem), C.POINTER(C.c_void_p), C.c_int32, C.c_double,
+                            C.c_double, C.c_int32, C.c_void_p], C.c_int32),
     "etb_index_and_update": ([C.c_void_p, C.c_size_t, C.POINTER(UpdateItem), C.c_int32, C.c_double,
                               C.c_int32, C.c_void_p], C.c_int32),
     "etb_uncompress": ([C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p,

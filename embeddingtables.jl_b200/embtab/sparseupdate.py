@@ -26,6 +26,25 @@ class Descent:
         self.eta = float(eta)
 
 
+class Adagrad:
+    """Row-wise Adagrad (GPU-only extension; the reference's update! knows Flux.Descent only).
+
+    One state element per table row, kept here per table (keyed by the table object) and created as zeros on
+    first use:  h = state[k] + mean(g.^2);  state[k] = h;  A[:, k] -= eta / (sqrt(h) + eps) * g, with g the
+    bucket's summed cotangent.  State arithmetic is Float32 (Float64 for Float64 tables)."""
+
+    def __init__(self, eta=0.1, eps=1e-8):
+        self.eta, self.eps = float(eta), float(eps)
+        self._state = {}
+
+    def state(self, table) -> DeviceArray:
+        st = self._state.get(id(table))
+        if st is None:
+            acc = np.float64 if table.dtype == np.float64 else np.float32
+            st = self._state[id(table)] = (DeviceArray.zeros((table.size(2),), acc), table)   # keeps the table alive
+        return st[0]
+
+
 class SparseEmbeddingUpdate:
     """SparseEmbeddingUpdate{S}(delta, indices): lazy, aliasing COO-like gradient
     (reference src/sparseupdate.jl:6-13).  `delta` (featuresize x batch, possibly a row-slice
@@ -214,7 +233,7 @@ def _flags(table) -> int:
     return f
 
 
-def _apply(tables, grads, indexer, eta):
+def _apply(tables, grads, indexer, eta, opt=None):
     """update!(table, update, indexer, alpha): apply an already-indexed update.  The cotangent applied is
     the one of the updates passed HERE (reference src/sparseupdate.jl:131-154 reads `update.delta`); the
     indexer only has to hold index! of the same index arrays."""
@@ -228,6 +247,11 @@ def _apply(tables, grads, indexer, eta):
     flags = _lib.UPDATE_SPLIT_LONG if _ORDER["mode"] == "split" else 0   # FMA travels per item
     stream = C.c_void_p(current_stream_ptr())
     base._items = (_lib.UpdateItem * len(items))(*items)
+    if isinstance(opt, Adagrad):
+        states = (C.c_void_p * len(items))(*[opt.state(t).ptr for t in tables])
+        _lib.check(_lib.lib().etb_adagrad_update(C.byref(view), base._items, states, len(items), opt.eta, opt.eps,
+                                                 flags, stream))
+        return
     _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(items), float(eta), flags, stream))
 
 
@@ -237,7 +261,7 @@ def update_table_(table, update: SparseEmbeddingUpdate, indexer, alpha, nontempo
     _apply([table], [update], indexer, alpha)
 
 
-def update_(opt: Descent, table, grad, indexer=None, nontemporal=True, *args, num_splits=4, nthreads=None,
+def update_(opt, table, grad, indexer=None, nontemporal=True, *args, num_splits=4, nthreads=None,
             scratchspaces=None, telemetry_cb=None):
     """update!(opt::Descent, table, grad, [indexer], [Val(nontemporal)]) for one table
     (src/sparseupdate.jl:160-178) and update!(opt, tables, grads, indexers; num_splits, nthreads,
@@ -249,7 +273,7 @@ def update_(opt: Descent, table, grad, indexer=None, nontemporal=True, *args, nu
             indexer = Indexer()
         if not _consume_prefetch(indexer, [table], [grad]):
             index_(indexer, table, grad)
-        _apply([table], [grad], indexer, opt.eta)  # convert(eltype(table), opt.eta) happens in the kernel
+        _apply([table], [grad], indexer, opt.eta, opt)  # convert(eltype(table), opt.eta) happens in the kernel
         return None
     tables, grads = list(table), list(grad)
     indexers = indexer if indexer is not None else [Indexer()]
@@ -258,7 +282,7 @@ def update_(opt: Descent, table, grad, indexer=None, nontemporal=True, *args, nu
         index_(ix, tables, grads)  # one batched sort for every table (the @batch index! phase, :211-213)
     if telemetry_cb is not None:
         telemetry_cb()
-    _apply(tables, grads, ix, opt.eta)
+    _apply(tables, grads, ix, opt.eta, opt)
     return None
 
 

@@ -242,6 +242,20 @@ int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item
 int32_t etb_sgd_update(const etb_index_view* view_host, const etb_update_item* items_host,
                        int32_t n_items, double eta, int32_t flags, void* stream);
 
+/* Optimiser extension (the reference's update! exists for Flux.Descent only,
+ * src/sparseupdate.jl:160-189): row-wise Adagrad on the same buckets.  `states_host` is a host array of n_items
+ * device pointers; states_host[t] holds one element per row of table t, in the table's arithmetic type
+ * (Float32 for Float32 / Float16 / BFloat16 tables, Float64 for Float64 tables), zero before the first step.
+ * For every bucket, with g = its summed cotangent (accumulated exactly as etb_sgd_update does):
+ *     h = state[k] + (sum_d g_d^2) / dim;   state[k] = h;   A[:, k] -= (eta / (sqrt(h) + eps)) * g
+ * every operation rounded separately, the sum of squares in a fixed order (per lane, then an XOR butterfly over
+ * the lanes of the row -- oracle/oracle.py adagrad_update restates it), so results are deterministic.
+ * Rows must fit one pass of the kernel (up to 128 vectors: 2 KB with 16-byte alignment), else ETB_ERR_UNSUPPORTED.
+ * ETB_UPDATE_FMA is ignored; ETB_UPDATE_SPLIT_LONG applies to the summation of g as usual. */
+int32_t etb_adagrad_update(const etb_index_view* view_host, const etb_update_item* items_host,
+                           void* const* states_host, int32_t n_items, double eta, double eps, int32_t flags,
+                           void* stream);
+
 /* update!(opt, table(s), grad(s)): etb_index followed by etb_sgd_update
  * (reference src/sparseupdate.jl:160-178). */
 int32_t etb_index_and_update(void* workspace, size_t workspace_bytes,

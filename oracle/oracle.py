@@ -332,3 +332,54 @@ def update_lowp(data, delta, I, eta):
         row = data[:, r - 1].astype(np.float32)
         data[:, r - 1] = (row - eta32 * a).astype(data.dtype)
     return data
+
+
+# ------------------------------------------------------------------ row-wise Adagrad extension
+# etb_adagrad_update has NO reference counterpart either (the reference's update! exists for
+# Flux.Descent only): PARITY UNPINNED; this function DEFINES the semantics stated in include/embtab_b200.h and
+# repeats the kernel's fixed summation order for the sum of squares (element d lives in vector d // NE, vector v
+# on lane v % G in slot v // G; each lane adds its squares slot by slot, element by element; the G lanes are then
+# combined by an XOR butterfly), every operation rounded separately.
+def adagrad_layout(dim, itemsize, vb=None):
+    rowbytes = dim * itemsize
+    if vb is None:  # dense, aligned tables and cotangents: the widest vector that divides the row
+        vb = next((v for v in (16, 8) if v >= itemsize and rowbytes % v == 0), 8 if itemsize == 8 else 4)
+    nvec = rowbytes // vb
+    G = min(32, 1 << max(0, (nvec - 1).bit_length()))
+    return nvec, G, vb // itemsize
+
+
+def adagrad_update(data, state, delta, I, eta, eps, vb=None):
+    """in place on `data` (featuresize x nrows) and `state` (nrows, float32 -- float64 for float64 tables)"""
+    A = np.float64 if data.dtype == np.float64 else np.float32
+    assert state.dtype == A
+    I = np.asarray(I, dtype=np.int64)
+    bag = I.shape[0] if I.ndim == 2 else 1
+    flat = I.reshape(-1, order="F")
+    dim = data.shape[0]
+    nvec, G, NE = adagrad_layout(dim, data.dtype.itemsize, vb)
+    slots = -(-nvec // G)
+    assert slots <= 4, "rows of more than 128 vectors are unsupported"
+    acc = {}
+    for p, r in enumerate(flat.tolist()):
+        d = np.asarray(delta[:, p // bag]).astype(A)
+        acc[r] = (acc[r] + d) if r in acc else (A(0) + d)
+    lanes = np.arange(G)
+    for r, g in acc.items():
+        gp = np.zeros(slots * G * NE, A)
+        gp[:dim] = g
+        gp = gp.reshape(slots, G, NE)
+        s = np.zeros(G, A)
+        for p in range(slots):
+            for e in range(NE):
+                s = s + gp[p, :, e] * gp[p, :, e]
+        off = G >> 1
+        while off:
+            s = s + s[lanes ^ off]
+            off >>= 1
+        h = A(state[r - 1] + A(s[0] / A(dim)))
+        state[r - 1] = h
+        scale = A(A(eta) / A(np.sqrt(h) + A(eps)))
+        row = data[:, r - 1].astype(A)
+        data[:, r - 1] = (row - scale * g).astype(data.dtype)
+    return data
