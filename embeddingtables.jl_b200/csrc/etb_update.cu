@@ -378,10 +378,13 @@ __device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
 // element ascending), then the G lanes of the group are combined by an XOR butterfly (offsets G/2 ... 1); a + b is
 // commutative, so every lane ends with the same bits.  Lanes past the row (`on[p]` false) contribute nothing.
 // Called by all lanes of the group together; the row must fit one pass (nvec <= G * VPL, checked by the host).
+// The caller loads `state_old` together with the table row (one bucket = one writer, so nothing changes it in
+// between) -- loading it here would put a dependent DRAM round trip at the end of every bucket.
 template <typename T, int VB, int VPL>
 __device__ __forceinline__ void adagrad_apply(Vec<T, VB> (&out)[VPL], const Vec<T, VB> (&old)[VPL],
                                               const AccVec<T, VB> (&g)[VPL], const bool (&on)[VPL], acc_t<T>* state,
-                                              acc_t<T> eta, acc_t<T> eps, int dim, int G, int gl, unsigned gmask) {
+                                              acc_t<T> state_old, acc_t<T> eta, acc_t<T> eps, int dim, int G, int gl,
+                                              unsigned gmask) {
     using A = acc_t<T>;
     A s = A(0);
 #pragma unroll
@@ -390,8 +393,7 @@ __device__ __forceinline__ void adagrad_apply(Vec<T, VB> (&out)[VPL], const Vec<
 #pragma unroll
             for (int e = 0; e < Vec<T, VB>::NE; ++e) s = add_rn(s, mul_rn(g[p].e[e], g[p].e[e]));
     for (int off = G >> 1; off > 0; off >>= 1) s = add_rn(s, __shfl_xor_sync(gmask, s, off));
-    const A h = add_rn(*state, div_rn(s, (A)dim));
-    __syncwarp(gmask);  // every lane has read the old state before lane 0 replaces it
+    const A h = add_rn(state_old, div_rn(s, (A)dim));  // state_old: loaded by the caller with the row, long before
     if (gl == 0) *state = h;
     const A scale = div_rn(eta, add_rn(sqrt_rn(h), eps));
 #pragma unroll
@@ -541,10 +543,16 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
             for (int k0 = 0; k0 < G; k0 += UB) {
                 // the old table row and the first delta row of UB buckets, all in flight together
                 V old[UB][VPL], v0[UB][VPL];
+                acc_t<T> st_old[OPT == kOptAdagrad ? UB : 1];
+                (void)st_old;
 #pragma unroll
                 for (int u = 0; u < UB; ++u) {
                     if (k0 + u < G && s_meta2[gbase + k0 + u].cnt > 0) {
                         const TileMeta m = s_meta[gbase + k0 + u];
+                        if constexpr (OPT == kOptAdagrad) {
+                            const TileMeta2 q = s_meta2[gbase + k0 + u];
+                            st_old[u] = *((const acc_t<T>*)P.state[q.slot] + q.pad);
+                        }
 #pragma unroll
                         for (int p = 0; p < VPL; ++p) {
                             ld_plain<VB>(&old[u][p], m.row + vi[p]);
@@ -582,8 +590,9 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
 #pragma unroll
                                 for (int p = 0; p < VPL; ++p) on[p] = gl + p * G < nvec;
                                 V out[VPL];
-                                adagrad_apply<T, VB, VPL>(out, old[u], acc, on, (acc_t<T>*)P.state[m2.slot] + m2.pad, eta,
-                                                          (acc_t<T>)P.eps, nvec * V::NE, G, gl, gmask);
+                                adagrad_apply<T, VB, VPL>(out, old[u], acc, on, (acc_t<T>*)P.state[m2.slot] + m2.pad,
+                                                          st_old[OPT == kOptAdagrad ? u : 0], eta, (acc_t<T>)P.eps,
+                                                          nvec * V::NE, G, gl, gmask);
 #pragma unroll
                                 for (int p = 0; p < VPL; ++p)
                                     if (on[p]) st_plain<VB>(row + vi[p], &out[p]);
@@ -660,10 +669,19 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         AccVec<T, VB> acc[UB][VPL];
         V first[kSame ? 1 : UB][kSame ? 1 : VPL];
         (void)first;
+        // Adagrad: the state element comes in with the row (a load at the end of the bucket would be a dependent
+        // DRAM round trip); the half types have no registers to spare for that (measured: a 16-byte spill costs more)
+        constexpr bool kEarlyState = OPT == kOptAdagrad && sizeof(T) >= 4;
+        acc_t<T> st_old[kEarlyState ? UB : 1];
+        (void)st_old;
 #pragma unroll
         for (int u = 0; u < UB; ++u) {
             if (s_meta2[gbase + k0 + u].cnt > 0) {
                 const TileMeta m = s_meta[gbase + k0 + u];
+                if constexpr (kEarlyState) {
+                    const TileMeta2 q = s_meta2[gbase + k0 + u];
+                    st_old[u] = *((const acc_t<T>*)P.state[q.slot] + q.pad);
+                }
 #pragma unroll
                 for (int p = 0; p < VPL; ++p) {
                     if (on[p]) {
@@ -712,8 +730,9 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
                     }
                 } else {
                     V out[VPL];
-                    adagrad_apply<T, VB, VPL>(out, old[u], acc[u], on, (acc_t<T>*)P.state[m2.slot] + m2.pad, eta,
-                                              (acc_t<T>)P.eps, P.nvec * V::NE, G, lane & (G - 1), group_mask(G, lane));
+                    acc_t<T>* state = (acc_t<T>*)P.state[m2.slot] + m2.pad;
+                    adagrad_apply<T, VB, VPL>(out, old[u], acc[u], on, state, kEarlyState ? st_old[kEarlyState ? u : 0] : *state,
+                                              eta, (acc_t<T>)P.eps, P.nvec * V::NE, G, lane & (G - 1), group_mask(G, lane));
 #pragma unroll
                     for (int p = 0; p < VPL; ++p)
                         if (on[p]) st_plain<VB>(row + p * G * VB, &out[p]);
@@ -766,6 +785,12 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
             for (int p = 0; p < VPL; ++p) vi[p] = min(pass0 + gl + p * G, nvec - 1) * VB;
             V old[VPL];
             AccVec<T, VB> acc[VPL];
+            acc_t<T>* state = nullptr;
+            acc_t<T> st_old = acc_t<T>(0);
+            if (OPT == kOptAdagrad && medium) {
+                state = (acc_t<T>*)P.state[(int)(rec.key >> P.row_bits) - P.slot0] + (int64_t)(rec.key & row_mask);
+                st_old = *state;
+            }
 #pragma unroll
             for (int p = 0; p < VPL; ++p) {
                 if (medium) ld_plain<VB>(&old[p], row + vi[p]);
@@ -777,9 +802,7 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
 #pragma unroll
                 for (int p = 0; p < VPL; ++p) on[p] = gl + p * G < nvec;
                 V out[VPL];
-                const int slot = (int)(rec.key >> P.row_bits) - P.slot0;
-                adagrad_apply<T, VB, VPL>(out, old, acc, on, (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask), eta,
-                                          (acc_t<T>)P.eps, nvec * V::NE, G, gl, gmask);
+                adagrad_apply<T, VB, VPL>(out, old, acc, on, state, st_old, eta, (acc_t<T>)P.eps, nvec * V::NE, G, gl, gmask);
 #pragma unroll
                 for (int p = 0; p < VPL; ++p)
                     if (on[p]) st_plain<VB>(row + vi[p], &out[p]);
@@ -879,9 +902,9 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
                     }
                 } else {  // single pass (host-checked); group 0 = the first G lanes of warp 0
                     V out[VPL];
-                    const int slot = (int)(rec.key >> P.row_bits) - P.slot0;
-                    adagrad_apply<T, VB, VPL>(out, old, tot, on, (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask), eta,
-                                              (acc_t<T>)P.eps, nvec * V::NE, G, gl, group_mask(G, threadIdx.x & 31));
+                    acc_t<T>* state = (acc_t<T>*)P.state[(int)(rec.key >> P.row_bits) - P.slot0] + (int64_t)(rec.key & row_mask);
+                    adagrad_apply<T, VB, VPL>(out, old, tot, on, state, *state, eta, (acc_t<T>)P.eps, nvec * V::NE, G, gl,
+                                              group_mask(G, threadIdx.x & 31));
 #pragma unroll
                     for (int p = 0; p < VPL; ++p)
                         if (on[p]) st_plain<VB>(row + vi[p], &out[p]);
