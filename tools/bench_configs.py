@@ -264,20 +264,20 @@ def config_lowp(fh):
             tables.append(E.SimpleEmbedding(E.DeviceArray(buf, (dim, nrows)), E.Static(dim)))
         out = E.DeviceArray.empty((128 + nt * dim, batch), ndt)
         strategy = E.PreallocationStrategy(128)
-        t_f = timeit(lambda: E.maplookup_(strategy, out, tables, I), iters=10, warmup=3)
+        t_f = timeit_graph(lambda: E.maplookup_(strategy, out, tables, I), iters=10, warmup=3)   # GPU time (the eager call is host-bound here)
         delta = E.DeviceArray(torch.randn(nt * dim * batch, device="cuda").to(tdt), (nt * dim, batch))
         grads = [E.SparseEmbeddingUpdate(E.Static(dim), delta.rows(k * dim, (k + 1) * dim), i) for k, i in enumerate(Is)]
         indexer = E.Indexer()
         E.index_(indexer, tables, grads)
-        t_k = timeit(lambda: E.sparseupdate._apply(tables, grads, indexer, 0.01), iters=10, warmup=3)
-        t_i = timeit(lambda: E.index_(indexer, tables, grads), iters=10, warmup=3)
+        t_k = timeit_graph(lambda: E.sparseupdate._apply(tables, grads, indexer, 0.01), iters=10, warmup=3)
+        t_i = timeit_graph(lambda: E.index_(indexer, tables, grads), iters=10, warmup=3)
         fb = nt * batch * (bag * (8 + dim * es) + dim * es)
         ub = nt * batch * dim * es + 2 * u * dim * es + nt * batch * bag * 4
         step = t_f + t_i + t_k
         opt = E.Adagrad(0.01, 1e-8)
         for t in tables:
             opt.state(t)                                     # allocate the state vectors outside the timed region
-        t_a = timeit(lambda: E.sparseupdate._apply(tables, grads, indexer, 0.01, opt), iters=10, warmup=3)
+        t_a = timeit_graph(lambda: E.sparseupdate._apply(tables, grads, indexer, 0.01, opt), iters=10, warmup=3)
         ab = ub + 2 * u * 4                                   # + state read-modify-write, one Float32 per distinct row
         emit({"config": "c2-adagrad", "dtype": name, "update_ms": t_a, "sgd_update_ms": t_k, "update_gbs": ab / t_a / 1e6,
               "update_frac_of_measured_peak": ab / t_a / 1e6 / PEAK}, fh)

@@ -94,6 +94,7 @@ Every number comes from `gpurun` runs on B200s of this pool.  The `.ncu-rep` fil
 | `r1_ubench_random_rmw_ceiling.json` | `tools/ubench_rmw.cu`: what HBM delivers for random 512-byte RMW / reads |
 | `r1_c1_*.jsonl`, `r1_c3_*.jsonl`, `r1_c4_*.jsonl`, `r1_c5_sweep.jsonl` | `tools/bench_configs.py`: the other BASELINE configs |
 | `r1_c2_lowp.jsonl` | `tools/bench_configs.py --config lowp`: C2's shape with Float16 / BFloat16 tables (extension) beside Float32 |
+| `r1_lowp_ncu_kernels.json` | ncu per-launch time / DRAM bytes / registers of the Float32, Float16, BFloat16 forward and update (SGD, Adagrad) kernels on C2's shape |
 | `r1_zero_copy_probe.jsonl` | `tools/zero_copy_probe.py`: kernels reading / writing pinned host buffers directly |
 
 compute-sanitizer is closed on this pool (`gpurun` refuses it); `tools/sanitize_smoke.py` (a pass over every kernel
