@@ -192,20 +192,27 @@ __global__ void __launch_bounds__(kRsThreads, ETB_RS_MIN_BLOCKS) rs_scatter_kern
         carry_g += tot;
     }
     __syncthreads();
-    // reorder the tile by digit in shared memory (stable); the values are only needed now, so they are
-    // loaded here (16 independent coalesced loads) instead of occupying registers during the ranking
-    int32_t v[kRsItems];
+    // reorder the tile by digit in shared memory (stable).  The values are only needed now and the keys are read
+    // again (from L2: this CTA loaded them a moment ago) instead of being held in registers across the ranking and
+    // the scans -- 64 registers per thread then hold everything without spilling.  Two halves of 8 loads each.
 #pragma unroll
-    for (int i = 0; i < kRsItems; ++i) {
-        const int q = warp * (32 * kRsItems) + i * 32 + lane;
-        v[i] = q < tile_n ? __ldg(vin + tile_base + q) : 0;
-    }
+    for (int h = 0; h < 2; ++h) {
+        KeyT k2[kRsItems / 2];
+        int32_t v[kRsItems / 2];
 #pragma unroll
-    for (int i = 0; i < kRsItems; ++i) {
-        const uint32_t d = dr[i] >> 16;
-        if (d != 0xffffu) {
-            const uint32_t q2 = tstart[d] + wcount[warp * kRsMaxBins + d] + (dr[i] & 0xffffu);
-            spair[q2] = RsPair<KeyT>{k[i], v[i]};
+        for (int i = 0; i < kRsItems / 2; ++i) {
+            const int q = warp * (32 * kRsItems) + (h * (kRsItems / 2) + i) * 32 + lane;
+            k2[i] = q < tile_n ? __ldg(kin + tile_base + q) : (KeyT)0;
+            v[i] = q < tile_n ? __ldg(vin + tile_base + q) : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < kRsItems / 2; ++i) {
+            const uint32_t dri = dr[h * (kRsItems / 2) + i];
+            const uint32_t d = dri >> 16;
+            if (d != 0xffffu) {
+                const uint32_t q2 = tstart[d] + wcount[warp * kRsMaxBins + d] + (dri & 0xffffu);
+                spair[q2] = RsPair<KeyT>{k2[i], v[i]};
+            }
         }
     }
     __syncthreads();
