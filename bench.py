@@ -109,58 +109,96 @@ class ClockSampler:
                            "samples": len(sm)}
 
 
+def common_config(world, dist):
+    """`config` of the JSON line: what the workload IS.  Both arms (ours / --impl reference) emit exactly this
+    dict for the same --gpus/--dist; how each arm schedules it is reported outside `config`."""
+    nt = NT * world
+    w = WORKLOAD if world == 1 else (
+        WORKLOAD + f"; weak scaling over {world} GPUs: {NT} tables per GPU ({nt} in the ensemble), global batch {BATCH}, "
+        "tables block-partitioned table-wise, pooled outputs / cotangents exchanged all-to-all")
+    return {"workload": w, "dist": dist, "tables": nt, "rows": NROWS, "dim": DIM, "bag": BAG, "batch": BATCH,
+            "prependrows": PREPEND, "index_type": "int64", "eta": ETA,
+            "l2": "inputs larger than L2: 13.3 GB of tables per GPU, random rows; no flush needed"}
+
+
 # ----------------------------------------------------------------------------------- CPU arm
-def cpu_reference_arm(steps, warmup, dist, sample_tables=4):
-    """The reference's CPU path (C port = oracle/) on this box's host cores: PreallocationStrategy
-    forward (8 batch chunks x tables behind an atomic counter) + ensemble update! (index! per table,
-    then 4 bucket splits x tables behind an atomic counter), all host threads.  Bounded sample:
-    `sample_tables` of the 26 tables at the full batch/bag/dim (cost is linear in tables)."""
+def cpu_reference_arm(steps, warmup, dist, world=1):
+    """The reference's CPU path (C port = oracle/; the reference is Julia, which this image cannot run) on this
+    box's host cores, on the FULL ensemble of the workload: PreallocationStrategy forward (8 batch chunks x tables
+    behind an atomic counter, reference src/lookup.jl:316-371) + ensemble update! (index! per table in parallel,
+    then num_splits = 4 bucket splits x tables behind an atomic counter, src/sparseupdate.jl:199-238), one pinned
+    worker thread per core.  Every table is there because the reference's index! phase is table-parallel only
+    (:211-213): a sample of a few tables would leave most cores idle in the phase that dominates the step.
+    The update is timed with both Indexer flavours of the reference (SparseIndexer = its default, DenseIndexer);
+    the faster one is reported."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     O.build()
-    cores = os.cpu_count() or 1
+    cores = O.allowed_cpus()
+    O.set_pinning(True)
+    nt_full = NT * world
+    nt = nt_full
+    try:   # N > 1 (weak scaling: 26 tables per GPU): as many of the tables as half of the free host RAM holds
+        import psutil
+        per_table = DIM * NROWS * 4 + 5 * BAG * BATCH * 8 + 2 * DIM * BATCH * 4
+        nt = int(max(NT, min(nt_full, psutil.virtual_memory().available * 0.5 // per_table)))
+    except Exception:
+        nt = min(nt_full, NT)
     rng = np.random.default_rng(SEED)
-    nt = sample_tables
     tables = []
-    for _ in range(nt):
+    for t in range(nt):
         a = np.empty((DIM, NROWS), np.float32, order="F")
-        a.reshape(-1, order="F")[:] = rng.random(DIM * NROWS, dtype=np.float32)
+        O.fill_uniform(a, SEED + t, cores)          # uniform [0, 1) like the reference's tests; first touch by the workers
         tables.append(O.Table(a, static=True))
-    I = make_indices(rng, dist, nt, NROWS, BAG, BATCH)
-    Is = [np.asfortranarray(I[:, :, t]) for t in range(nt)]
+    Is = []
+    for t0 in range(0, nt, NT):                      # same generator as the GPU arm, NT tables at a time
+        I = make_indices(rng, dist, min(NT, nt - t0), NROWS, BAG, BATCH)
+        Is += [np.asfortranarray(I[:, :, t]) for t in range(I.shape[2])]
     out = np.zeros((PREPEND + nt * DIM, BATCH), np.float32, order="F")
-    delta = np.asfortranarray(rng.standard_normal(out.shape, dtype=np.float32))
+    delta = np.empty(out.shape, np.float32, order="F")
+    O.fill_uniform(delta, SEED - 1, cores)           # values do not matter for the timing
+    delta -= 0.5
     deltas = [delta[PREPEND + DIM * k: PREPEND + DIM * (k + 1)] for k in range(nt)]
-    scratch = O.alloc_indexers(Is)  # caller-owned Indexers, reused like the reference's
+    scratch = O.alloc_indexers(Is)                   # caller-owned Indexers, reused like the reference's
     lookups = nt * BATCH * BAG
-    t_fwd, t_upd = [], []
+    t_fwd, t_upd = [], {False: [], True: []}
     for s in range(warmup + steps):
         t0 = time.perf_counter()
         O.maplookup("preallocation", tables, Is, prependrows=PREPEND, nthreads=cores, out=out)
         t1 = time.perf_counter()
-        O.update_ensemble(tables, deltas, Is, ETA, num_splits=4, nthreads=cores, scratch=scratch)
+        O.update_ensemble(tables, deltas, Is, ETA, num_splits=4, nthreads=cores, scratch=scratch, dense=False)
         t2 = time.perf_counter()
         if s >= warmup:
-            t_fwd.append(t1 - t0); t_upd.append(t2 - t1)
-    step_s = float(np.mean(t_fwd) + np.mean(t_upd))
-    return {"value": lookups / step_s, "unit": "lookups/s", "cores": cores, "kind": "port",
-            "sample": f"{nt} of {NT} tables (1M x 128 f32), full batch {BATCH}, bag {BAG}, {dist} indices; "
-                      f"{steps} timed steps after {warmup} warm-up; C port of the reference (Julia absent), "
-                      f"AVX-512={bool(O.lib().etbo_uses_avx512())}",
-            "ms_per_step": step_s * 1e3, "fwd_ms": float(np.mean(t_fwd)) * 1e3, "update_ms": float(np.mean(t_upd)) * 1e3,
-            "lookups_per_step": lookups}
+            t_fwd.append(t1 - t0); t_upd[False].append(t2 - t1)
+    for s in range(1 + min(steps, 3)):               # the DenseIndexer flavour of the same update
+        t1 = time.perf_counter()
+        O.update_ensemble(tables, deltas, Is, ETA, num_splits=4, nthreads=cores, scratch=scratch, dense=True)
+        if s >= 1:
+            t_upd[True].append(time.perf_counter() - t1)
+    upd = {k: float(np.mean(v)) for k, v in t_upd.items()}
+    dense = upd[True] < upd[False]
+    step_s = float(np.mean(t_fwd)) + upd[dense]
+    sample = (f"all {nt} tables" if nt == nt_full else f"{nt} of {nt_full} tables (host RAM)") + \
+        (f" (1M x 128 f32, {nt * DIM * NROWS * 4 / 1e9:.1f} GB), full batch {BATCH}, bag {BAG}, {dist} indices; "
+         f"{steps} timed steps after {warmup} warm-up; {cores} pinned threads; C port of the reference (Julia absent), "
+         f"AVX-512={bool(O.lib().etbo_uses_avx512())}; update! with the {'Dense' if dense else 'Sparse'}Indexer "
+         f"(sparse {upd[False] * 1e3:.1f} ms, dense {upd[True] * 1e3:.1f} ms)")
+    return {"value": lookups / step_s, "unit": "lookups/s", "cores": cores, "kind": "port", "sample": sample,
+            "ms_per_step": step_s * 1e3, "fwd_ms": float(np.mean(t_fwd)) * 1e3, "update_ms": upd[dense] * 1e3,
+            "lookups_per_step": lookups, "tables": nt}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    r = cpu_reference_arm(steps, warmup, args.dist)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    r = cpu_reference_arm(steps, warmup, args.dist, world)
     line = {"impl": "reference", "metric": "embedding_lookups_per_sec", "value": r["value"], "unit": "lookups/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "dist": args.dist, "note": "bounded sample; lookups/s is per-table linear"},
+            "config": common_config(world, args.dist),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"], "gpu_launches": 0}
@@ -180,6 +218,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    args._numa = bind_to_gpu_numa(local) if (world > 1 or os.environ.get("ETB_BIND_NUMA")) else None
     E._lib.check(E.lib().etb_init(local))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -372,17 +411,16 @@ def run_ours(args):
             "frac": kernels[dom]["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
             "frac_of_nominal_8TBs": kernels[dom]["gbs"] / 8000.0}
 
-    cpu = cpu_reference_arm(steps=2, warmup=1, dist=args.dist) if not args.no_cpu_baseline else None
+    cpu = cpu_reference_arm(steps=3, warmup=1, dist=args.dist) if not args.no_cpu_baseline else None
     gpu_launches = (launches["fwd"] + launches["index"] + launches["update"]) * K
     line = {
         "metric": "embedding_lookups_per_sec", "value": lookups / (ms_per_step * 1e-3), "unit": "lookups/s",
         "n_gpus": 1, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "dist": args.dist, "index_type": "int64", "eta": ETA,
-                   "schedule": "index! on a side stream overlapping the forward" if overlap else "phases back to back",
-                   "ms_per_step_phases_back_to_back": serial_ms,
-                   "l2": "inputs larger than L2: 13.3 GB of tables, random rows; no flush needed",
-                   "distinct_rows_per_table_mean": u_sum / NT},
+        "config": common_config(1, args.dist),
+        "schedule": "index! on a side stream overlapping the forward" if overlap else "phases back to back",
+        "ms_per_step_phases_back_to_back": serial_ms,
+        "distinct_rows_per_table_mean": u_sum / NT,
         "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
                 "d2h_bytes_per_step": int(out_pinned.nbytes),
@@ -402,6 +440,36 @@ def run_ours(args):
     emit_line(line)
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process (and so the first touch of its pinned buffers) to the CPUs of the NUMA node the GPU hangs
+    off: with N ranks pulling host buffers through one box, remote-node traffic is what saturates first."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as e:  # no sysfs / no such attribute: run unbound
+        return {"numa_node": None, "error": str(e)[:80]}
+
+
+def rank_delta_block(q, owner, rows, cols):
+    """cotangent rows of `owner`'s tables at rank q (rows x cols of q's batch slice): a seed per (rank, owner) so
+    that any rank can regenerate what a peer sent it (the self-check below)"""
+    return np.random.default_rng(SEED + 7919 * (q + 1) + owner).standard_normal((rows, cols), dtype=np.float32)
+
+
 def run_sharded(args, rank, world, local):
     """N > 1: table-wise sharding (north star / SURVEY 8e).  Weak scaling: every rank owns 26 tables
     (26*N in the ensemble), the global batch stays 16384, every rank looks its tables up for the
@@ -415,6 +483,7 @@ def run_sharded(args, rank, world, local):
     from embtab.dist import ShardedEnsemble, ShardPlan
 
     lib = E.lib()
+    numa = getattr(args, "_numa", None)
     rng = np.random.default_rng(SEED + 1000 * rank)
     gen = torch.Generator(device="cuda").manual_seed(SEED + rank)
     tables = []
@@ -422,7 +491,10 @@ def run_sharded(args, rank, world, local):
         buf = torch.rand(DIM * NROWS, device="cuda", dtype=torch.float32, generator=gen)
         tables.append(E.SimpleEmbedding(E.DeviceArray(buf, (DIM, NROWS)), E.Static(DIM)))
     plan = ShardPlan([DIM] * (NT * world), world, rank, PREPEND, BATCH)
-    ens = ShardedEnsemble(tables, plan, fused=not args.nccl_a2a)
+    fused = not args.nccl_a2a
+    G = max(1, int(os.environ.get("ETB_TABLE_GROUPS", "4"))) if fused else 1
+    ens = ShardedEnsemble(tables, plan, fused=fused, table_groups=G, peer_barrier=not args.nccl_barrier)
+    G = ens.n_groups
     I_host = make_indices(rng, args.dist, NT, NROWS, BAG, BATCH)
     idx_pinned = E.pinned_empty((BAG, BATCH, NT), np.int64)
     idx_pinned[...] = I_host
@@ -430,32 +502,119 @@ def run_sharded(args, rank, world, local):
     out_shape = (plan.total_rows, plan.my_cols)
     out_pinned = E.pinned_empty(out_shape, np.float32)
     delta_pinned = E.pinned_empty(out_shape, np.float32)
-    delta_pinned.reshape(-1, order="F")[:] = rng.standard_normal(out_shape[0] * out_shape[1], dtype=np.float32)
+    delta_pinned[:PREPEND] = 0.0
+    for o in range(world):
+        delta_pinned[plan.row_off[o]:plan.row_off[o] + plan.rows[o]] = rank_delta_block(rank, o, plan.rows[o], plan.my_cols)
     delta_dev = E.DeviceArray.empty(out_shape, np.float32).upload(delta_pinned)
     opt = E.Descent(ETA)
     launches = [0]
 
-    def step(events=None):
+    def step(events=None, pipelined=True):
         ens.forward(I_dev)
-        n = ens.launches
+        n = ens.launches + (1 if ens.peer_barrier else 0)
         if events: events[1].record()
-        grads = ens.backward(delta_dev)
-        n += 1
-        if events: events[2].record()
-        ens.update_(opt, grads)
-        n += lib.etb_last_launch_count() + ens.index_launches   # update kernels + the prefetched index! launches
-        if events: events[3].record()
+        if pipelined:      # backward exchange and update!, table group by table group
+            ens.backward_update_(opt, delta_dev)
+            n += ens.update_launches + ens.index_launches + 2 * G
+            if events: events[2].record(); events[3].record()
+        else:
+            grads = ens.backward(delta_dev)
+            n += 2
+            if events: events[2].record()
+            ens.update_(opt, grads)
+            n += lib.etb_last_launch_count() * G + ens.index_launches
+            if events: events[3].record()
         launches[0] = n
 
-    # e2e: indices and cotangent in from pinned host memory, this rank's feature-matrix columns out, every step.
-    # Not pipelined: with N ranks pulling through one host the PCIe legs are host-bound (double-buffering the
-    # index upload was measured at N = 2 and changed nothing).
+    # ---- self-check before anything is timed (uniform runs): one table block that a PEER looked up for me and one of
+    # MY tables after a whole step, against a single-GPU recomputation from regenerated inputs
+    check = "skipped"
+    if args.dist == "uniform" and not args.no_self_check:
+        q = (rank + 1) % world                                            # a peer: its first table, my columns
+        genq = torch.Generator(device="cuda").manual_seed(SEED + q)
+        tq = E.SimpleEmbedding(E.DeviceArray(torch.rand(DIM * NROWS, device="cuda", dtype=torch.float32, generator=genq),
+                                             (DIM, NROWS)), E.Static(DIM))
+        Iq = make_indices(np.random.default_rng(SEED + 1000 * q), args.dist, NT, NROWS, BAG, BATCH)[:, plan.clo[rank]:plan.chi[rank], 0]
+        t0_before = tables[0].to_numpy()
+        step()
+        torch.cuda.synchronize()
+        want = E.lookup(tq, np.asfortranarray(Iq)).numpy()
+        got = ens.out.rows(plan.row_off[q], plan.row_off[q] + DIM).numpy()
+        ok = np.array_equal(got, want)
+        del tq
+        ref = E.SimpleEmbedding(t0_before, E.Static(DIM))                 # my first table, updated on one GPU
+        dglob = np.concatenate([rank_delta_block(p_, rank, plan.rows[rank], plan.cols[p_])[:DIM] for p_ in range(world)], axis=1)
+        E.update_(opt, ref, E.SparseEmbeddingUpdate(E.Static(DIM), np.asfortranarray(dglob), np.asfortranarray(I_host[:, :, 0])))
+        torch.cuda.synchronize()
+        ok = ok and np.array_equal(ref.to_numpy(), tables[0].to_numpy())
+        flag = torch.tensor([0 if ok else 1], device="cuda")
+        dist.all_reduce(flag)
+        check = "ok" if flag.item() == 0 else "FAILED"
+        print(f"[rank {rank}] dist check {'ok' if ok else 'FAILED'}: block of peer {q} and my updated table 0 "
+              f"{'equal' if ok else 'DIFFER from'} the single-GPU recomputation", file=sys.stderr, flush=True)
+        if check != "ok":
+            raise SystemExit("bench.py: sharded self-check failed")
+        del ref
+        torch.cuda.empty_cache()
+
+    # ---- e2e: indices and cotangent in from pinned host memory, this rank's feature-matrix columns out, every
+    # step, pipelined like the N = 1 path: indices double-buffered (step k+1's upload beside step k's download), the
+    # forward in column chunks whose D2H overlaps the next chunk's lookup, the cotangent in table-group row slices
+    # (one strided copy per owner and group), each group's exchange + update! as its slice has landed.
+    copy_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    E2E_CHUNKS = 4 if fused else 1
+    I_buf = [I_dev, E.DeviceArray.empty((BAG, BATCH, NT), np.int64)]
+    idx_ready, buf_free, e2e_state = [None, None], [None, None], {"k": 0}
+    cb = [round(c * plan.my_cols / E2E_CHUNKS) for c in range(E2E_CHUNKS + 1)]
+
+    def upload_indices(slot):
+        with torch.cuda.stream(copy_stream):
+            if buf_free[slot] is not None:
+                copy_stream.wait_event(buf_free[slot])
+            I_buf[slot].upload(idx_pinned)
+            idx_ready[slot] = copy_stream.record_event()
+
     def step_e2e():
-        I_dev.upload(idx_pinned)
-        ens.forward(I_dev)
-        ens.out.download(out_pinned)
-        delta_dev.upload(delta_pinned)
-        ens.update_(opt, ens.backward(delta_dev))
+        if not fused:      # NCCL variant: the plain chain
+            I_dev.upload(idx_pinned)
+            ens.forward(I_dev)
+            ens.out.download(out_pinned)
+            delta_dev.upload(delta_pinned)
+            ens.update_(opt, ens.backward(delta_dev))
+            return
+        k = e2e_state["k"]
+        slot = k % 2
+        if idx_ready[slot] is None:
+            upload_indices(slot)
+        main = torch.cuda.current_stream()
+        main.wait_event(idx_ready[slot])
+        idx_ready[slot] = None
+        for c in range(E2E_CHUNKS):
+            ens.forward(I_buf[slot], cols=(cb[c], cb[c + 1]), prefetch_index=(c == 0))
+            done = main.record_event()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                ens.out.cols(cb[c], cb[c + 1]).download(out_pinned[:, cb[c]:cb[c + 1]])
+        upload_indices(1 - slot)
+        landed = []
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_stream(d2h_stream)            # the host has the whole result before the cotangent exists
+            for g in range(G):
+                for o in range(world):
+                    r0 = plan.row_off[o] + ens.group_rows[o][g][0]
+                    r1 = r0 + ens.group_rows[o][g][1]
+                    if g == 0 and o == 0:
+                        r0 = 0                             # the dense part's rows travel too: the whole matrix is copied
+                    delta_dev.rows(r0, r1).upload(delta_pinned[r0:r1])
+                landed.append(copy_stream.record_event())
+        ens.update_launches = 0
+        for g in range(G):
+            main.wait_event(landed[g])
+            ens.scatter_group(delta_dev, g)
+            ens.update_group_(opt, g)
+        ens.join_updates()
+        buf_free[slot] = main.record_event()
+        e2e_state["k"] = k + 1
 
     def sync():
         torch.cuda.synchronize()
@@ -468,20 +627,26 @@ def run_sharded(args, rank, world, local):
         step()
     sync()
     K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    end = torch.cuda.Event(enable_timing=True)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    start.record()
     for k in range(K):
-        ev[k][0].record()
-        step(ev[k])
+        step()
     end.record()
     sync()
-    t = torch.tensor([ev[0][0].elapsed_time(end) / K,
+    # phases: the same step with the backward exchange and the update back to back (not pipelined)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    for k in range(K):
+        ev[k][0].record()
+        step(ev[k], pipelined=False)
+    sync()
+    t = torch.tensor([start.elapsed_time(end) / K,
                       float(np.mean([e[0].elapsed_time(e[1]) for e in ev])),
                       float(np.mean([e[1].elapsed_time(e[2]) for e in ev])),
-                      float(np.mean([e[2].elapsed_time(e[3]) for e in ev]))], device="cuda", dtype=torch.float64)
+                      float(np.mean([e[2].elapsed_time(e[3]) for e in ev])),
+                      float(np.mean([e[0].elapsed_time(e[3]) for e in ev]))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)          # max over ranks, device-timed
-    ms_per_step, fwd_ms, bwd_ms, upd_ms = t.tolist()
+    ms_per_step, fwd_ms, bwd_ms, upd_ms, serial_ms = t.tolist()
 
     for _ in range(2):
         step_e2e()
@@ -508,24 +673,30 @@ def run_sharded(args, rank, world, local):
             "metric": "embedding_lookups_per_sec", "value": lookups / (ms_per_step * 1e-3), "unit": "lookups/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD + f"; table-wise sharded: {NT} tables per GPU ({NT * world} total), global batch "
-                       f"{BATCH}, exchange = " + ("NCCL all-to-all + pack/unpack" if args.nccl_a2a else
-                       "fused: lookup/scatter kernels store into peer HBM over NVLink (CUDA IPC), all-reduce barrier"),
-                       "dist": args.dist, "index_type": "int64",
-                       "eta": ETA, "l2": "inputs larger than L2: 13.3 GB of tables per GPU, random rows; no flush needed"},
+            "config": common_config(world, args.dist),
+            "exchange": ("NCCL all-to-all + pack/unpack kernels" if args.nccl_a2a else
+                         "fused: lookup / scatter kernels store into peer HBM over NVLink (CUDA IPC); " +
+                         ("peer-memory flag barrier" if ens.peer_barrier else "NCCL all-reduce barrier") +
+                         f"; backward exchange + update! pipelined over {G} table groups"),
+            "self_check": check, "numa": numa,
             "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
-                    "d2h_bytes_per_step": int(out_pinned.nbytes)},
+                    "d2h_bytes_per_step": int(out_pinned.nbytes),
+                    "pipeline": ("indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent in %d "
+                                 "table-group row slices, each group's exchange + update! as its slice lands" % (E2E_CHUNKS, G))
+                                if fused else "plain chain"},
             "gpu_launches": launches[0] * K, "clocks": clocks.result,
             "roofline": {"bound": "hbm", "kernel": "pooled_kernel+a2a (fwd phase, max over ranks)",
                          "achieved": fwd_bytes / fwd_ms / 1e6, "peak": peak, "unit": "GB/s",
                          "frac": fwd_bytes / fwd_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src},
-            "phases_ms": {"fwd_lookup+exchange": fwd_ms, "bwd_exchange": bwd_ms, "index+update": upd_ms},
+            "phases_ms": {"fwd_lookup+exchange": fwd_ms, "bwd_exchange": bwd_ms, "index+update": upd_ms,
+                          "step_not_pipelined": serial_ms, "step_pipelined": ms_per_step},
             "nvlink": {"bytes_sent_per_rank_per_direction": a2a_bytes, "peak_gbs": 770.0,
                        "note": "phase times include the lookup / pack kernels; see profiles/ for the split"},
             "cpu_baseline": None,
         }
         emit_line(line)
+    ens.close()
     dist.destroy_process_group()
 
 
@@ -554,6 +725,9 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="run index! after the forward instead of beside it")
     ap.add_argument("--nccl-a2a", action="store_true",
                     help="N>1: exchange with NCCL all-to-all + pack/unpack instead of fused NVLink peer stores")
+    ap.add_argument("--nccl-barrier", action="store_true",
+                    help="N>1, fused exchange: a one-element NCCL all-reduce as barrier instead of the peer-memory flags")
+    ap.add_argument("--no-self-check", action="store_true", help="N>1: skip the sharded-vs-single-GPU check before timing")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

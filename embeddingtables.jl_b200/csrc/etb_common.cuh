@@ -43,7 +43,7 @@ inline bool elt_valid(int32_t elt) { return elt >= ETB_F32 && elt <= ETB_BF16; }
 inline bool elt_is_float(int32_t elt) { return elt == ETB_F32 || elt == ETB_F64 || elt == ETB_F16 || elt == ETB_BF16; }
 inline bool idx_elt_valid(int32_t e) { return e == ETB_I32 || e == ETB_I64; }
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+int num_sms();  // multiprocessors of the current device (148 on B200), queried once per thread and device
 
 inline int pow2ceil(int x) {
     int p = 1;

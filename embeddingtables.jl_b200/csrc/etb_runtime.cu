@@ -24,6 +24,18 @@ int32_t& launch_counter() {
     return n;
 }
 
+int num_sms() {
+    static thread_local int dev_cached = -1, sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return sms;
+    if (dev != dev_cached) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sms = v;
+        dev_cached = dev;
+    }
+    return sms;
+}
+
 int32_t validate_table(const etb_table& t, const char* who) {
     ETB_REQUIRE(elt_valid(t.elt), "%s: unsupported table element type %d", who, t.elt);
     ETB_REQUIRE(t.dim > 0, "%s: table dim must be positive (got %d)", who, t.dim);

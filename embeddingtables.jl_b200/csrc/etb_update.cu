@@ -1,6 +1,6 @@
 // etb_update.cu -- K4 index! (sort + segment) and K5 fused segment-reduce + SGD (sm_100a).
 //
-// Replaces the reference's Indexer (histogram!/prefixsum!/remap!, src/utils.jl:370-553 -- a
+// Replaces the reference's Indexer (histogram!/prefixsum!/remap!, src/utils.jl:131-314 -- a
 // stable counting sort of occurrence -> delta column by table row) and its update! kernels
 // (src/sparseupdate.jl:57-154, ensemble form :199-238).
 //
@@ -8,7 +8,7 @@
 //          key = t << row_bits | (index - 1),      value = delta column of p (= p / bag)
 // All items are sorted at once by a hand-written stable LSD radix sort restricted to the bits the
 // keys actually use (etb_sort.cuh), so members of a bucket stay in occurrence order = the order
-// remap! records (src/utils.jl:481-511).  Bucket starts are the positions whose key differs from the previous one,
+// remap! records (src/utils.jl:242-272).  Bucket starts are the positions whose key differs from the previous one,
 // compacted into one 16-byte record per bucket by three small hand-written kernels (count heads per
 // tile, scan the tile counts, write records).  Buckets come out in ascending (table, row) order instead
 // of the reference's first-seen order; buckets are disjoint table rows, so results do not
@@ -28,7 +28,7 @@
 #include <vector>
 
 #include "etb_common.cuh"
-#include "etb_sort.cuh"
+#include "etb_layout.cuh"
 
 namespace etb {
 
@@ -44,259 +44,6 @@ constexpr int kUThreads = 256;
 #define ETB_UPDATE_EXACT_MIN_BLOCKS 4
 #define ETB_UPDATE_USE_EXACT 1
 constexpr int kUMaxItems = 96;
-
-// ------------------------------------------------------------------------------------ layout
-// One record per bucket, written by K4 and read by K5 with ONE coalesced load per 32 buckets
-// (the reference's `cumulative` entry (col, offset), src/utils.jl:340-345, plus the first member).
-struct alignas(16) BucketRec {
-    uint32_t start;  // first sorted position of the bucket
-    int32_t m0;      // delta column of its first member
-    uint64_t key;    // slot << row_bits | (row - 1)
-};
-
-// Bucket classes of the update: SHORT (<= kShortMax members) finish inside the main kernel; MEDIUM
-// (kShortMax < members <= kLongThreshold, and every larger bucket in strict mode) become tasks of
-// bucket_tasks_kernel and are reduced strictly in order with 8 rows in flight; LONG (> kLongThreshold,
-// ETB_UPDATE_SPLIT_LONG only) are cut into kLongChunk-member chunk tasks whose partial rows
-// long_combine_kernel adds in a fixed order.
-constexpr int kShortMax = 4;
-constexpr int kLongThreshold = 128;  // buckets with more members than this are "long"
-constexpr int kLongChunk = 128;      // members per partial sum
-struct LongCounters { uint32_t n_long, n_chunks /* task cursor */, n_partials, pad; };
-struct LongRec { uint32_t bucket, chunk_base, nchunks, pad; };
-struct ChunkRec { uint32_t long_id, chunk; };  // long_id == kMediumTask: a MEDIUM bucket, chunk = its bucket index
-constexpr uint32_t kMediumTask = 0xffffffffu;
-
-struct IndexLayout {
-    int64_t n_total;
-    int32_t row_bits, slot_bits, key_bytes;
-    size_t max_long, max_chunks, max_medium, max_tasks, partial_pitch;
-    size_t off_keys[2], off_vals[2], off_recs, off_nnz, off_tiles, off_counters, off_long, off_chunks, off_partials,
-        off_temp, temp_bytes, total;
-};
-
-static int bits_for(uint64_t count) {  // bits needed to represent 0 .. count-1
-    int b = 0;
-    while (b < 63 && (1ull << b) < count) ++b;
-    return b;
-}
-
-static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
-
-// ---- bucket heads -> records (hand-written replacement of a library stream compaction) ----------
-// Position p is a bucket head when its key differs from the previous one.  Three small kernels:
-// count heads per 4096-position tile, scan the tile counts (one block), write one record per head
-// at its rank.  Positions are striped over the block (p = base + i*256 + tid) so every load is
-// coalesced; ranks follow position order (i-major, then warp, then lane) via warp ballots.
-constexpr int kSelThreads = 256, kSelItems = 16, kSelTile = kSelThreads * kSelItems;
-
-template <typename KeyT>
-__device__ __forceinline__ uint32_t head_flags(const KeyT* __restrict__ keys, int64_t base, int64_t n, KeyT (&k)[kSelItems]) {
-    uint32_t flags = 0;
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-        const int64_t p = base + i * kSelThreads + threadIdx.x;
-        if (p < n) {
-            k[i] = __ldg(keys + p);
-            if (p == 0 || __ldg(keys + p - 1) != k[i]) flags |= 1u << i;
-        }
-    }
-    return flags;
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kSelThreads) count_heads_kernel(const KeyT* __restrict__ keys, int64_t n,
-                                                                   uint32_t* __restrict__ tile_counts) {
-    __shared__ uint32_t warp_sums[kSelThreads / 32];
-    KeyT k[kSelItems];
-    uint32_t c = __popc(head_flags(keys, (int64_t)blockIdx.x * kSelTile, n, k));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-#pragma unroll
-        for (int w = 0; w < kSelThreads / 32; ++w) t += warp_sums[w];
-        tile_counts[blockIdx.x] = t;
-    }
-}
-
-// exclusive scan of the tile counts in place (one block of 1024 threads), total -> nnz
-__global__ void __launch_bounds__(1024) scan_tile_counts_kernel(uint32_t* __restrict__ counts, int ntiles,
-                                                                int64_t* __restrict__ nnz) {
-    __shared__ uint32_t warp_tot[32];
-    const int per = (ntiles + 1023) / 1024;
-    const int lo = min(threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
-    uint32_t sum = 0;
-    for (int i = lo; i < hi; ++i) sum += counts[i];
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += v;
-    }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        uint32_t w = warp_tot[threadIdx.x], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (threadIdx.x >= o) wi += v;
-        }
-        warp_tot[threadIdx.x] = wi - w;  // exclusive warp offsets
-        if (threadIdx.x == 31) *nnz = (int64_t)wi;
-    }
-    __syncthreads();
-    uint32_t run = warp_tot[threadIdx.x >> 5] + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t c = counts[i];
-        counts[i] = run;
-        run += c;
-    }
-}
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kSelThreads) write_records_kernel(const KeyT* __restrict__ keys,
-                                                                     const int32_t* __restrict__ map, int64_t n,
-                                                                     const uint32_t* __restrict__ tile_offsets,
-                                                                     BucketRec* __restrict__ recs) {
-    __shared__ uint32_t cnt[kSelItems][kSelThreads / 32];  // heads per (item row, warp), then exclusive offsets
-    const int64_t base = (int64_t)blockIdx.x * kSelTile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    KeyT k[kSelItems];
-    const uint32_t flags = head_flags(keys, base, n, k);
-    uint32_t before[kSelItems];  // heads of lower lanes in my warp, per item row
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-        const uint32_t ballot = __ballot_sync(0xffffffffu, (flags >> i) & 1u);
-        before[i] = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) cnt[i][warp] = __popc(ballot);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {  // exclusive scan of the 16 x 8 counts in position order (4 per lane)
-        constexpr int kCells = kSelItems * (kSelThreads / 32), kPer = kCells / 32;
-        uint32_t* flat = &cnt[0][0];
-        uint32_t v[kPer], sum = 0;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) { v[j] = flat[threadIdx.x * kPer + j]; sum += v[j]; }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) { flat[threadIdx.x * kPer + j] = run; run += v[j]; }
-    }
-    __syncthreads();
-    const uint32_t tile_off = tile_offsets[blockIdx.x];
-#pragma unroll
-    for (int i = 0; i < kSelItems; ++i) {
-        if ((flags >> i) & 1u) {
-            const int64_t p = base + i * kSelThreads + threadIdx.x;
-            BucketRec r;
-            r.start = (uint32_t)p;
-            r.m0 = __ldg(map + p);
-            r.key = (uint64_t)k[i];
-            recs[tile_off + cnt[i][warp] + before[i]] = r;
-        }
-    }
-}
-
-template <typename KeyT>
-static int32_t select_heads(uint32_t* tile_counts, const KeyT* keys, const int32_t* map, BucketRec* recs, int64_t* nnz,
-                            int64_t n, cudaStream_t stream) {
-    const int ntiles = (int)((n + kSelTile - 1) / kSelTile);
-    count_heads_kernel<KeyT><<<ntiles, kSelThreads, 0, stream>>>(keys, n, tile_counts);
-    ETB_LAUNCHED();
-    scan_tile_counts_kernel<<<1, 1024, 0, stream>>>(tile_counts, ntiles, nnz);
-    ETB_LAUNCHED();
-    write_records_kernel<KeyT><<<ntiles, kSelThreads, 0, stream>>>(keys, map, n, tile_counts, recs);
-    ETB_LAUNCHED();
-    return ETB_OK;
-}
-
-static int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexLayout& L) {
-    ETB_REQUIRE(n_items >= 0, "etb_index: negative item count");
-    ETB_REQUIRE(n_items == 0 || items, "etb_index: null items");
-    int64_t n_total = 0, max_rows = 1;
-    size_t max_row_bytes = 16;
-    for (int i = 0; i < n_items; ++i) {
-        const etb_update_item& it = items[i];
-        if (int32_t st = validate_table(it.table, "etb_index")) return st;
-        ETB_REQUIRE(idx_elt_valid(it.idx_elt), "etb_index: item %d: index type must be ETB_I32/ETB_I64", i);
-        ETB_REQUIRE(it.batch >= 0 && it.batch < 0x7fffffffll, "etb_index: item %d: bad batch %lld", i, (long long)it.batch);
-        ETB_REQUIRE(it.bag >= 0 && it.bag <= 0x7fffffffll, "etb_index: item %d: bad bag %lld", i, (long long)it.bag);
-        ETB_REQUIRE(it.bag == 0 || it.ld_idx >= it.bag, "etb_index: item %d: ld_idx < bag", i);
-        n_total += it.batch * (it.bag ? it.bag : 1);
-        max_rows = std::max(max_rows, it.table.nrows);
-        // partial rows of long buckets are kept in the arithmetic type (Float32 for the half types)
-        max_row_bytes = std::max(max_row_bytes, (size_t)it.table.dim * std::max<size_t>(4, elt_bytes(it.table.elt)));
-    }
-    ETB_REQUIRE(n_total < 0x7fffffffll, "etb_index: %lld occurrences exceed the 2^31 limit of one call", (long long)n_total);
-    L.n_total = n_total;
-    L.row_bits = std::max(1, bits_for((uint64_t)max_rows));
-    L.slot_bits = bits_for((uint64_t)std::max(1, n_items));
-    ETB_REQUIRE(L.row_bits + L.slot_bits <= 64, "etb_index: key does not fit 64 bits");
-    L.key_bytes = (L.row_bits + L.slot_bits <= 32) ? 4 : 8;
-    const size_t n = (size_t)std::max<int64_t>(n_total, 1);
-    L.max_long = n / kLongThreshold + 1;
-    L.max_medium = n / (kShortMax + 1) + 1;
-    L.max_chunks = n / kLongChunk + L.max_long;  // partial rows
-    L.max_tasks = L.max_chunks + L.max_medium;    // task list = long chunks + medium buckets
-    L.partial_pitch = align_up(max_row_bytes, 16);
-    size_t off = 0;
-    for (int b = 0; b < 2; ++b) { L.off_keys[b] = off; off = align_up(off + n * L.key_bytes); }
-    for (int b = 0; b < 2; ++b) { L.off_vals[b] = off; off = align_up(off + n * sizeof(int32_t)); }
-    L.off_recs = off; off = align_up(off + (n + 1) * sizeof(BucketRec));
-    L.off_nnz = off; off = align_up(off + sizeof(int64_t));
-    L.off_tiles = off; off = align_up(off + ((n + kSelTile - 1) / kSelTile + 1) * sizeof(uint32_t));
-    L.off_counters = off; off = align_up(off + sizeof(LongCounters));
-    L.off_long = off; off = align_up(off + L.max_long * sizeof(LongRec));
-    L.off_chunks = off; off = align_up(off + L.max_tasks * sizeof(ChunkRec));
-    L.off_partials = off; off = align_up(off + L.max_chunks * L.partial_pitch);
-    // scratch of the radix sort (tile histograms)
-    const size_t t_sort = rs_scratch_bytes((int64_t)n);
-    L.off_temp = off;
-    L.temp_bytes = t_sort;
-    L.total = align_up(off + L.temp_bytes);
-    return ETB_OK;
-}
-
-// ------------------------------------------------------------------------------------ K4a keys
-struct KeyDesc {
-    const void* idx;
-    int64_t start;   // first pair of this item in the concatenated arrays
-    uint32_t n;      // occurrences
-    uint32_t bag;    // 0 = vector
-    uint32_t ld_idx;
-    uint32_t pad;
-};
-struct KeyParams {
-    KeyDesc item[kUMaxItems];
-    int32_t row_bits;
-    int32_t slot0;  // slot number of item[0] (launches are chunked by kUMaxItems)
-};
-
-template <typename KeyT, typename IdxT>
-__global__ void __launch_bounds__(kUThreads)
-make_pairs_kernel(const __grid_constant__ KeyParams P, KeyT* __restrict__ keys, int32_t* __restrict__ vals) {
-    const KeyDesc& d = P.item[blockIdx.y];
-    const KeyT slot = (KeyT)(P.slot0 + blockIdx.y) << P.row_bits;
-    for (uint32_t p = blockIdx.x * kUThreads + threadIdx.x; p < d.n; p += gridDim.x * kUThreads) {
-        uint32_t col = p, pos = p;
-        if (d.bag) {  // flat column-major traversal (reference `columns`, src/utils.jl:312-320)
-            col = p / d.bag;
-            pos = col * d.ld_idx + (p - col * d.bag);
-        }
-        const int64_t i1 = (int64_t)__ldg((const IdxT*)d.idx + pos);
-        keys[d.start + p] = slot | (KeyT)(i1 - 1);
-        vals[d.start + p] = (int32_t)col;
-    }
-}
 
 // ------------------------------------------------------------------------------------ K5
 struct UpdDesc {  // 48 bytes
@@ -320,7 +67,7 @@ struct UpdParams {
     int32_t slot0, nslots;  // this launch handles slots [slot0, slot0 + nslots)
     int32_t G, nvec;
     int32_t fma, split_long;
-    int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:564-572
+    int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:325-333
     // row-wise Adagrad only (OPT == kOptAdagrad): per-item state vectors (one acc_t element per table row)
     double eps;
     char* state[kUMaxItems];
@@ -524,9 +271,14 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
             else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
         }
-        TileMeta m;
-        m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
-        m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
+        // addresses only for buckets this launch finishes itself: a padding lane or a bucket of another kernel
+        // class would pair item[0]'s table with a row of a different table (a Split table would then read its
+        // chunk-pointer array out of bounds)
+        TileMeta m{nullptr, nullptr};
+        if (cnt > 0) {
+            m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
+            m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
+        }
         s_meta[wbase + r * 32 + lane] = m;
         // pad: the SGD epilogue's FMA flag, or (Adagrad) the row number for the state vector
         s_meta2[wbase + r * 32 + lane] = TileMeta2{raw.x, cnt, mine ? slot : 0,
@@ -651,9 +403,11 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
             cnt = 0;
         }
         const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
-        TileMeta m;
-        m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
-        m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
+        TileMeta m{nullptr, nullptr};  // see sgd_update_kernel: no address arithmetic for buckets that are not mine
+        if (cnt > 0) {
+            m.row = row_ptr(md.table, (int64_t)(key & row_mask) + 1);
+            m.d0 = md.delta + (int64_t)(int32_t)raw.y * md.ld_delta_bytes;
+        }
         s_meta[threadIdx.x] = m;
         s_meta2[threadIdx.x] = TileMeta2{raw.x, cnt, mine ? slot : 0,
                                          OPT == kOptSgd ? (int32_t)md.table.pad : (int32_t)(key & row_mask)};
@@ -1023,98 +777,6 @@ static void launch_update(int opt, int which, const UpdClass& c, int grid, cudaS
     else launch_update_opt<kOptSgd>(which, c, grid, s, P);
 }
 
-static int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int32_t n_items,
-                          etb_index_view* view, cudaStream_t stream) {
-    IndexLayout L;
-    if (int32_t st = make_layout(items, n_items, L)) return st;
-    ETB_REQUIRE(ws != nullptr, "etb_index: null workspace");
-    ETB_REQUIRE(((uintptr_t)ws % 256) == 0, "etb_index: workspace must be 256-byte aligned");
-    if (ws_bytes < L.total)
-        return fail(ETB_ERR_WORKSPACE, "etb_index: workspace has %zu bytes, needs %zu", ws_bytes, L.total);
-    char* base = (char*)ws;
-    BucketRec* recs = (BucketRec*)(base + L.off_recs);
-    int64_t* nnz = (int64_t*)(base + L.off_nnz);
-    uint32_t* tiles = (uint32_t*)(base + L.off_tiles);
-    int32_t* vals[2] = {(int32_t*)(base + L.off_vals[0]), (int32_t*)(base + L.off_vals[1])};
-    void* keys[2] = {base + L.off_keys[0], base + L.off_keys[1]};
-    const int end_bit = L.row_bits + L.slot_bits;
-
-    if (L.n_total == 0) {
-        ETB_CUDA(cudaMemsetAsync(nnz, 0, sizeof(int64_t), stream));
-    } else {
-        // K4a: (key, delta column) pairs of every item
-        static thread_local KeyParams KP;
-        int64_t start = 0;
-        for (int i0 = 0; i0 < n_items; i0 += kUMaxItems) {
-            const int n = std::min(kUMaxItems, n_items - i0);
-            uint32_t max_n = 0;
-            int idx_elt = items[i0].idx_elt;
-            bool uniform_idx = true;
-            for (int j = 0; j < n; ++j) {
-                const etb_update_item& it = items[i0 + j];
-                KeyDesc& d = KP.item[j];
-                d.idx = it.idx;
-                d.start = start;
-                d.n = (uint32_t)(it.batch * (it.bag ? it.bag : 1));
-                d.bag = (uint32_t)it.bag;
-                d.ld_idx = (uint32_t)it.ld_idx;
-                d.pad = 0;
-                start += d.n;
-                max_n = std::max(max_n, d.n);
-                uniform_idx = uniform_idx && it.idx_elt == idx_elt;
-                ETB_REQUIRE(d.n == 0 || it.idx, "etb_index: item %d: null indices", i0 + j);
-            }
-            ETB_REQUIRE(uniform_idx, "etb_index: all items of one call must share the index element type");
-            if (max_n == 0) continue;
-            KP.row_bits = L.row_bits;
-            KP.slot0 = i0;
-            dim3 grid(std::min<uint32_t>((max_n + kUThreads - 1) / kUThreads, 8u * kNumSMs), (unsigned)n);
-            if (L.key_bytes == 4) {
-                if (idx_elt == ETB_I64) make_pairs_kernel<uint32_t, long long><<<grid, kUThreads, 0, stream>>>(KP, (uint32_t*)keys[0], vals[0]);
-                else make_pairs_kernel<uint32_t, int><<<grid, kUThreads, 0, stream>>>(KP, (uint32_t*)keys[0], vals[0]);
-            } else {
-                if (idx_elt == ETB_I64) make_pairs_kernel<uint64_t, long long><<<grid, kUThreads, 0, stream>>>(KP, (uint64_t*)keys[0], vals[0]);
-                else make_pairs_kernel<uint64_t, int><<<grid, kUThreads, 0, stream>>>(KP, (uint64_t*)keys[0], vals[0]);
-            }
-            ETB_LAUNCHED();
-        }
-        // K4b: stable radix sort over the used key bits (hand-written, etb_sort.cuh: 9/8/8-bit digits for C2's
-        // 25-bit keys = 3 passes), then one record per bucket head
-        int which = 0;
-        void* keys_out;
-        int32_t* vals_out;
-        if (L.key_bytes == 4) {
-            uint32_t* kb[2] = {(uint32_t*)keys[0], (uint32_t*)keys[1]};
-            if (int32_t st = radix_sort_pairs<uint32_t>(kb, vals, L.n_total, end_bit, (uint32_t*)(base + L.off_temp), stream, &which)) return st;
-        } else {
-            uint64_t* kb[2] = {(uint64_t*)keys[0], (uint64_t*)keys[1]};
-            if (int32_t st = radix_sort_pairs<uint64_t>(kb, vals, L.n_total, end_bit, (uint32_t*)(base + L.off_temp), stream, &which)) return st;
-        }
-        keys_out = keys[which];
-        vals_out = vals[which];
-        keys[0] = keys_out;
-        if (L.key_bytes == 4) {
-            if (int32_t st = select_heads<uint32_t>(tiles, (const uint32_t*)keys[0], vals_out, recs, nnz, L.n_total, stream)) return st;
-        } else {
-            if (int32_t st = select_heads<uint64_t>(tiles, (const uint64_t*)keys[0], vals_out, recs, nnz, L.n_total, stream)) return st;
-        }
-        vals[0] = vals_out;
-    }
-    if (view) {
-        view->keys = keys[0];
-        view->map = vals[0];
-        view->records = recs;
-        view->nnz = nnz;
-        view->scratch = base + L.off_counters;
-        view->n_total = L.n_total;
-        view->key_bytes = L.key_bytes;
-        view->row_bits = L.row_bits;
-        view->num_splits = 0;
-        view->this_split = 0;
-    }
-    return ETB_OK;
-}
-
 static int32_t update_impl(const etb_index_view* view, const etb_update_item* items, int32_t n_items, double eta,
                            int32_t flags, cudaStream_t stream, int opt = kOptSgd, void* const* states = nullptr,
                            double eps = 0.0) {
@@ -1191,13 +853,13 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         const int64_t per_block = kUThreads / c.G;
         if (view->n_total > kShortMax) {  // medium buckets + long-bucket chunks: one task kernel
             const int64_t max_tasks = view->n_total / (kShortMax + 1) + 1;
-            const int gridT = (int)std::min<int64_t>((max_tasks + per_block - 1) / per_block, (int64_t)kNumSMs * 8);
+            const int gridT = (int)std::min<int64_t>((max_tasks + per_block - 1) / per_block, (int64_t)num_sms() * 8);
             launch_update(opt, kKernelTasks, c, gridT, stream, P);
             ETB_LAUNCHED();
         }
         if (P.split_long && view->n_total > kLongThreshold) {
             const int64_t max_long = view->n_total / kLongThreshold + 1;
-            const int gridB = (int)std::min<int64_t>(max_long, (int64_t)kNumSMs * 4);  // one CTA per long bucket
+            const int gridB = (int)std::min<int64_t>(max_long, (int64_t)num_sms() * 4);  // one CTA per long bucket
             launch_update(opt, kKernelCombine, c, gridB, stream, P);
             ETB_LAUNCHED();
         }
@@ -1228,7 +890,8 @@ __global__ void uncompress_kernel(T* dst, int64_t ld_dst, int dim, const T* delt
 struct A2ABlocks {
     int64_t rows[16];
     int64_t row_off[16];
-    char* dense[16];  // block r's dense (rows[r] x batch_local) matrix: local buffer or peer memory
+    int64_t dense_ld_bytes[16];  // bytes between the columns of block r's destination (rows[r] * es when dense)
+    char* dense[16];  // block r's (rows[r] x batch_local) matrix: local buffer or peer memory
 };
 
 template <int VB, bool UNPACK>
@@ -1243,7 +906,7 @@ a2a_copy_kernel(char* strided, int64_t ld_bytes, const __grid_constant__ A2ABloc
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t col = t / vec_per_col, v = t - col * vec_per_col;
         char* s = sbase + col * ld_bytes + v * VB;
-        char* d = dbase + col * row_bytes + v * VB;
+        char* d = dbase + col * B.dense_ld_bytes[r] + v * VB;
         Vec<uint32_t, VB> x;
         if (UNPACK) { ld_row<VB>(&x, d); st_stream<VB>(s, &x); }
         else { ld_row<VB>(&x, s); st_stream<VB>(d, &x); }
@@ -1252,7 +915,8 @@ a2a_copy_kernel(char* strided, int64_t ld_bytes, const __grid_constant__ A2ABloc
 
 // dense == nullptr: per-block destinations in dense_ptrs (peer memory); else blocks laid end to end in `dense`
 static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, void* const* dense_ptrs, const int64_t* rows,
-                        const int64_t* row_off, int32_t nranks, int64_t batch_local, int32_t elt, cudaStream_t stream) {
+                        const int64_t* row_off, int32_t nranks, int64_t batch_local, int32_t elt, cudaStream_t stream,
+                        const int64_t* dense_ld = nullptr) {
     launch_counter() = 0;
     ETB_REQUIRE(nranks >= 1 && nranks <= 16, "etb_a2a: nranks must be in 1..16");
     ETB_REQUIRE(elt_valid(elt), "etb_a2a: bad element type");
@@ -1266,16 +930,18 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, voi
         B.rows[r] = rows[r];
         B.row_off[r] = row_off[r];
         B.dense[r] = dense ? (char*)dense + off * es : (char*)dense_ptrs[r];
+        B.dense_ld_bytes[r] = (dense_ld ? dense_ld[r] : rows[r]) * es;
         ETB_REQUIRE(B.dense[r] || rows[r] == 0, "etb_a2a: null block pointer");
+        ETB_REQUIRE(!dense_ld || dense_ld[r] >= rows[r], "etb_a2a: destination leading dimension smaller than the block");
         off += rows[r] * batch_local;
         max_rows = std::max(max_rows, rows[r]);
-        while (vb > es && ((rows[r] * es) % vb || (row_off[r] * es) % vb || (uintptr_t)B.dense[r] % vb)) vb >>= 1;
+        while (vb > es && ((rows[r] * es) % vb || (row_off[r] * es) % vb || (uintptr_t)B.dense[r] % vb || B.dense_ld_bytes[r] % vb)) vb >>= 1;
     }
     while (vb > es && ((ld * es) % vb || (uintptr_t)strided % vb)) vb >>= 1;
     if (vb < 4) return fail(ETB_ERR_UNSUPPORTED, "etb_a2a: half-precision blocks must be 4-byte aligned (even row counts and offsets)");
     if (max_rows == 0) return ETB_OK;
     const int64_t total = max_rows * es / vb * batch_local;
-    dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 8), (unsigned)nranks);
+    dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8), (unsigned)nranks);
     const int64_t ldb = ld * es;
 #define ETB_A2A(VBV)                                                                                          \
     if (unpack) a2a_copy_kernel<VBV, true><<<grid, 256, 0, stream>>>((char*)strided, ldb, B, batch_local, es); \
@@ -1286,25 +952,28 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, voi
     return ETB_OK;
 }
 
+// ------------------------------------------------------------------------------------ peer-memory barrier
+// One warp: lane r tells rank r "rank `me` has reached `epoch`" with a release store into r's flag array (peer
+// memory over NVLink), then waits until rank r has told me the same.  The kernels before this one on the stream
+// have completed, so their peer stores are ordered before the flag; the kernels after it see every peer's data.
+struct PeerFlags { uint32_t* flags[16]; };
+__global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags F, int me, int nranks, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r < nranks) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(F.flags[r] + me), "r"(epoch) : "memory");
+        uint32_t v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(F.flags[me] + r) : "memory");
+        } while ((int32_t)(v - epoch) < 0);
+    }
+}
+
 }  // namespace etb
 
 using namespace etb;
 
 extern "C" {
-
-int32_t etb_index_workspace_bytes(const etb_update_item* items_host, int32_t n_items, size_t* bytes_host) {
-    ETB_REQUIRE(bytes_host, "etb_index_workspace_bytes: null output");
-    IndexLayout L;
-    if (int32_t st = make_layout(items_host, n_items, L)) return st;
-    *bytes_host = L.total;
-    return ETB_OK;
-}
-
-int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item* items_host, int32_t n_items,
-                  etb_index_view* view_host, void* stream) {
-    launch_counter() = 0;
-    return index_impl(workspace, workspace_bytes, items_host, n_items, view_host, (cudaStream_t)stream);
-}
 
 int32_t etb_sgd_update(const etb_index_view* view_host, const etb_update_item* items_host, int32_t n_items, double eta,
                        int32_t flags, void* stream) {
@@ -1365,6 +1034,26 @@ int32_t etb_a2a_scatter(void* const* dst_ptrs_host, const void* src, int64_t ld_
                         const int64_t* row_off_host, int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
     return a2a_copy(false, const_cast<void*>(src), ld_src, nullptr, dst_ptrs_host, rows_host, row_off_host, nranks,
                     batch_local, elt, (cudaStream_t)stream);
+}
+
+int32_t etb_a2a_scatter_ld(void* const* dst_ptrs_host, const int64_t* dst_ld_host, const void* src, int64_t ld_src,
+                           const int64_t* rows_host, const int64_t* row_off_host, int32_t nranks, int64_t batch_local,
+                           int32_t elt, void* stream) {
+    ETB_REQUIRE(dst_ld_host, "etb_a2a_scatter_ld: null leading dimensions");
+    return a2a_copy(false, const_cast<void*>(src), ld_src, nullptr, dst_ptrs_host, rows_host, row_off_host, nranks,
+                    batch_local, elt, (cudaStream_t)stream, dst_ld_host);
+}
+
+int32_t etb_peer_barrier(void* const* flag_ptrs_host, int32_t rank, int32_t nranks, uint32_t epoch, void* stream) {
+    launch_counter() = 0;
+    ETB_REQUIRE(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, "etb_peer_barrier: bad rank %d of %d", rank, nranks);
+    ETB_REQUIRE(flag_ptrs_host, "etb_peer_barrier: null flag pointers");
+    PeerFlags F;
+    for (int r = 0; r < 16; ++r) F.flags[r] = r < nranks ? (uint32_t*)flag_ptrs_host[r] : nullptr;
+    for (int r = 0; r < nranks; ++r) ETB_REQUIRE(F.flags[r], "etb_peer_barrier: null flag array of rank %d", r);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(F, rank, nranks, epoch);
+    ETB_LAUNCHED();
+    return ETB_OK;
 }
 
 }  // extern "C"

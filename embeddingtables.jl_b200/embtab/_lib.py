@@ -87,6 +87,9 @@ _SIGS = {
     "etb_ipc_close": ([C.c_void_p], C.c_int32),
     "etb_a2a_scatter": ([C.POINTER(C.c_void_p), C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                          C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
+    "etb_a2a_scatter_ld": ([C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
+                            C.POINTER(C.c_int64), C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
+    "etb_peer_barrier": ([C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p], C.c_int32),
     "etb_a2a_pack": ([C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                       C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
 }

@@ -5,7 +5,7 @@ Here they live in device memory allocated through PyTorch (device memory / strea
 things torch is used for); shapes are Julia shapes, memory order is Julia's, so pointers and
 leading dimensions go straight into the C ABI.  2-d arrays may be row-slice views of a parent
 (leading dimension > rows) -- what `view(dst, rows, :)` is in the reference's
-PreallocationStrategy (src/lookup.jl:336-340) and its pullback (src/utils.jl:289-302).
+PreallocationStrategy (src/lookup.jl:336-340) and its pullback (src/utils.jl:50-63).
 """
 from __future__ import annotations
 

@@ -111,12 +111,16 @@ class ShardedEnsemble:
     update_(opt, grads)
     """
 
-    def __init__(self, tables_local, plan: ShardPlan, group=None, fused: bool = False):
+    def __init__(self, tables_local, plan: ShardPlan, group=None, fused: bool = False, table_groups: int = 1,
+                 peer_barrier: bool = True):
         """fused=False: NCCL all-to-all + pack/unpack kernels.  fused=True: the lookup kernel stores
         straight into the peers' feature matrices and the backward scatter straight into the owners'
-        cotangent buffers over NVLink (CUDA-IPC mapped peer memory); the only collective left is a
-        one-element all-reduce used as a stream-ordered barrier."""
+        cotangent buffers over NVLink (CUDA-IPC mapped peer memory); ranks meet at a hand-written
+        barrier over peer-memory flags (etb_peer_barrier; peer_barrier=False: a one-element NCCL
+        all-reduce instead).  table_groups > 1 (fused only): backward_update_ sends the cotangent
+        table group by table group and every owner updates group g while group g+1 is on the wire."""
         self.tables, self.plan, self.group, self.fused = list(tables_local), plan, group, bool(fused)
+        self.peer_barrier = bool(peer_barrier) and self.fused
         assert len(self.tables) == len(plan.my_tables)
         if not self.tables:
             raise ValueError("every rank must own at least one table (fewer tables than ranks)")
@@ -128,11 +132,25 @@ class ShardedEnsemble:
         self.delta_global = DeviceArray.empty((max(1, p.my_rows), p.batch_global), self.dtype)
         self.out = DeviceArray.empty((p.total_rows, p.my_cols), self.dtype)
         self.indexer = Indexer()
+        # table groups of the pipelined backward: every owner q cuts ITS tables into the same number of contiguous
+        # groups; group_rows[q][g] = (first feature row inside q's block, rows) of q's group g
+        G = max(1, min(int(table_groups), min(b - a for a, b in zip(p.tlo, p.thi)))) if self.fused else 1
+        self.group_bounds, self.group_rows = [], []
+        for q in range(p.world):
+            nq = p.thi[q] - p.tlo[q]
+            b = [round(g * nq / G) for g in range(G + 1)]
+            self.group_bounds.append(b)
+            offs = np.concatenate([[0], np.cumsum(p.dims[p.tlo[q]:p.thi[q]])]).astype(int)
+            self.group_rows.append([(int(offs[b[g]]), int(offs[b[g + 1]] - offs[b[g]])) for g in range(G)])
+        self.n_groups = G
+        self.group_indexers = [Indexer() for _ in range(G)] if G > 1 else [self.indexer]
+        self._upd_stream = None
         self._I = None
         self._rows = (C.c_int64 * p.world)(*p.rows)
         self._row_off = (C.c_int64 * p.world)(*p.row_off)
         self.launches = 0
         self.index_launches = 0
+        self.update_launches = 0
         if self.fused:
             self._setup_peer_memory()
 
@@ -140,31 +158,36 @@ class ShardedEnsemble:
     def _setup_peer_memory(self):
         p, lib, es = self.plan, _lib.lib(), np.dtype(self.dtype).itemsize
         max_cols = max(p.cols)
-        sizes = [p.total_rows * max_cols * es, max(1, p.my_rows) * p.batch_global * es]
+        sizes = [p.total_rows * max_cols * es, max(1, p.my_rows) * p.batch_global * es, 256]   # out, cotangent, flags
         self._raw = []
         for nbytes in sizes:                               # raw cudaMalloc: an IPC handle maps a whole allocation
             ptr = C.c_void_p()
             _lib.check(lib.etb_malloc(C.byref(ptr), max(nbytes, 256)))
             self._raw.append(ptr.value)
-        handles = np.zeros(2 * 64, np.uint8)
+        _lib.check(lib.etb_memset(self._raw[2], 0, 256, C.c_void_p(current_stream_ptr())))   # barrier flags start at 0
+        torch.cuda.current_stream().synchronize()
+        NB = len(sizes)
+        handles = np.zeros(NB * 64, np.uint8)
         for k, ptr in enumerate(self._raw):
             _lib.check(lib.etb_ipc_export(ptr, handles[64 * k:].ctypes.data))
         mine = torch.from_numpy(handles).cuda()
         gathered = [torch.empty_like(mine) for _ in range(p.world)]
         dist.all_gather(gathered, mine, group=self.group)
-        self._peer_out, self._peer_dglob, self._imported = [], [], []
+        self._peer_out, self._peer_dglob, self._peer_flags, self._imported = [], [], [], []
         for q in range(p.world):
             if q == p.rank:
-                self._peer_out.append(self._raw[0]); self._peer_dglob.append(self._raw[1])
+                self._peer_out.append(self._raw[0]); self._peer_dglob.append(self._raw[1]); self._peer_flags.append(self._raw[2])
                 continue
             h = gathered[q].cpu().numpy()
             ptrs = []
-            for k in range(2):
+            for k in range(NB):
                 ptr = C.c_void_p()
                 _lib.check(lib.etb_ipc_import(np.ascontiguousarray(h[64 * k:64 * k + 64]).ctypes.data, C.byref(ptr)))
                 ptrs.append(ptr.value)
                 self._imported.append(ptr.value)
-            self._peer_out.append(ptrs[0]); self._peer_dglob.append(ptrs[1])
+            self._peer_out.append(ptrs[0]); self._peer_dglob.append(ptrs[1]); self._peer_flags.append(ptrs[2])
+        self._flag_ptrs = (C.c_void_p * p.world)(*self._peer_flags)
+        self._epoch = 0
         # my own buffers, as DeviceArrays over the raw allocations
         self.out = DeviceArray.from_pointer(self._raw[0], (p.total_rows, p.my_cols), self.dtype)
         self.delta_global = DeviceArray.from_pointer(self._raw[1], (max(1, p.my_rows), p.batch_global), self.dtype)
@@ -180,12 +203,28 @@ class ShardedEnsemble:
                                                       for q in self._order])
         self._scatter_rows = (C.c_int64 * p.world)(*[p.rows[q] for q in self._order])
         self._scatter_row_off = (C.c_int64 * p.world)(*[p.row_off[q] for q in self._order])
+        # the same per table group: row block (group_rows) of owner q inside its row block, destination = that row
+        # block inside q's (rows[q] x B_global) cotangent buffer (leading dimension rows[q])
+        self._gscatter = []
+        for g in range(self.n_groups):
+            ptrs = (C.c_void_p * p.world)(*[self._peer_dglob[q] + (self.group_rows[q][g][0] + p.clo[p.rank] * p.rows[q]) * es
+                                            for q in self._order])
+            lds = (C.c_int64 * p.world)(*[max(1, p.rows[q]) for q in self._order])
+            rows = (C.c_int64 * p.world)(*[self.group_rows[q][g][1] for q in self._order])
+            offs = (C.c_int64 * p.world)(*[p.row_off[q] + self.group_rows[q][g][0] for q in self._order])
+            self._gscatter.append((ptrs, lds, rows, offs))
+        self._upd_stream = torch.cuda.Stream()
         dist.barrier(group=self.group)
 
     def _barrier(self):
         """stream-ordered barrier: completes on this rank's stream only after every rank's preceding
         kernels (whose completion makes their peer stores visible) have finished."""
-        dist.all_reduce(self._flag, group=self.group)
+        if self.peer_barrier:
+            self._epoch = (self._epoch + 1) & 0xffffffff
+            _lib.check(_lib.lib().etb_peer_barrier(self._flag_ptrs, self.plan.rank, self.plan.world, self._epoch,
+                                                   C.c_void_p(current_stream_ptr())))
+        else:
+            dist.all_reduce(self._flag, group=self.group)
 
     def close(self):
         if self.fused:
@@ -197,15 +236,18 @@ class ShardedEnsemble:
                 _lib.lib().etb_free(ptr)
             self._imported, self._raw, self.fused = [], [], False
 
-    def _forward_fused(self, Is):
+    def _forward_fused(self, Is, cols=None):
+        """cols = (c0, c1): only local columns c0..c1 of every rank's slice (the e2e path looks the batch up in column
+        chunks so that a chunk can travel to the host while the next one is computed)"""
         p = self.plan
         items, off = [], 0
         for t, i in zip(self.tables, Is):
             f = featuresize(t)
             for q in self._order:                         # my rows of peer q's feature matrix, q's columns
-                if p.cols[q]:
-                    dst = self._peer_out_arrays[q].rows(p.row_off[p.rank] + off, p.row_off[p.rank] + off + f)
-                    items.append(_item(t, i.cols(p.clo[q], p.chi[q]), dst))
+                c0, c1 = (0, p.cols[q]) if cols is None else (min(cols[0], p.cols[q]), min(cols[1], p.cols[q]))
+                if c1 > c0:
+                    dst = self._peer_out_arrays[q].rows(p.row_off[p.rank] + off, p.row_off[p.rank] + off + f).cols(c0, c1)
+                    items.append(_item(t, i.cols(p.clo[q] + c0, p.clo[q] + c1), dst))
             off += f
         if items:
             _run(items)
@@ -252,17 +294,22 @@ class ShardedEnsemble:
         per = bag * p.batch_global
         return [DeviceArray(glob, shape, t * per, None, np_dtype) for t in range(t_mine)]
 
-    def forward(self, I, out: DeviceArray = None, prefetch_index: bool = True) -> DeviceArray:
+    def forward(self, I, out: DeviceArray = None, prefetch_index: bool = True, cols=None) -> DeviceArray:
         p = self.plan
         Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else
                                              [I.lastdim(t) for t in range(I.shape[-1])])]
         self._I = Is
         if prefetch_index:   # index! needs only the indices: run it beside the lookup and the exchange
-            _prefetch_index(self.indexer, self.tables, Is)
-            self.index_launches = _lib.lib().etb_last_launch_count()
+            self.index_launches = 0
+            b = self.group_bounds[p.rank]
+            for g, ix in enumerate(self.group_indexers):
+                a0, a1 = (b[g], b[g + 1]) if self.n_groups > 1 else (0, len(self.tables))
+                _prefetch_index(ix, self.tables[a0:a1], Is[a0:a1])
+                self.index_launches += _lib.lib().etb_last_launch_count()
         if self.fused:
             assert out is None, "fused mode writes into the peer-mapped self.out"
-            return self._forward_fused(Is)
+            return self._forward_fused(Is, cols)
+        assert cols is None
         out = self.out if out is None else out
         # Peer p's send block is (my_rows x cols[p]) dense at element offset my_rows*clo[p]: the
         # blocks laid end to end ARE the column-major (my_rows x B_global) matrix of my tables'
@@ -306,4 +353,45 @@ class ShardedEnsemble:
         return grads
 
     def update_(self, opt, grads):
-        update_(opt, self.tables, grads, [self.indexer])
+        if self.n_groups == 1:
+            update_(opt, self.tables, grads, [self.indexer])
+            return
+        b = self.group_bounds[self.plan.rank]
+        for g, ix in enumerate(self.group_indexers):
+            update_(opt, self.tables[b[g]:b[g + 1]], grads[b[g]:b[g + 1]], [ix])
+
+    def scatter_group(self, delta: DeviceArray, g: int):
+        """backward exchange of table group g alone: my cotangent's rows of every owner's group g go into that
+        owner's buffer (fused mode), followed by the barrier"""
+        p = self.plan
+        ptrs, lds, rows, offs = self._gscatter[g]
+        _lib.check(_lib.lib().etb_a2a_scatter_ld(ptrs, lds, delta.ptr, delta.ld, rows, offs, p.world, p.my_cols, delta.elt,
+                                                 C.c_void_p(current_stream_ptr())))
+        self._barrier()
+
+    def update_group_(self, opt, g: int):
+        """update! of my tables of group g on the update stream, as soon as the main stream's barrier for that
+        group has passed; call join_updates() before the tables are used again"""
+        b = self.group_bounds[self.plan.rank]
+        grads = self._grads()[b[g]:b[g + 1]]
+        ev = torch.cuda.current_stream().record_event()
+        self._upd_stream.wait_event(ev)
+        with torch.cuda.stream(self._upd_stream):
+            update_(opt, self.tables[b[g]:b[g + 1]], grads, [self.group_indexers[g]])
+        self.update_launches += _lib.lib().etb_last_launch_count()
+
+    def join_updates(self):
+        torch.cuda.current_stream().wait_stream(self._upd_stream)
+
+    def backward_update_(self, opt, delta: DeviceArray):
+        """backward + update!, pipelined over table groups (fused mode): while the owners update group g the
+        cotangent of group g+1 crosses NVLink.  Same results as backward() followed by update_()."""
+        self.update_launches = 0
+        if not self.fused or self.n_groups == 1:
+            self.update_(opt, self.backward(delta))
+            self.update_launches = _lib.lib().etb_last_launch_count()
+            return
+        for g in range(self.n_groups):
+            self.scatter_group(delta, g)
+            self.update_group_(opt, g)
+        self.join_updates()

@@ -2,7 +2,7 @@
 
 Mirrors reference src/sparseupdate.jl (SparseEmbeddingUpdate :6-13, uncompress :16-32, rrule
 :35-40, update! kernels :46-154, Flux compat :160-189, ensemble update :195-238), the rrules of
-src/lookup.jl:247-258, 374-389, and `Slicer`/`Indexer`/`IndexerView` of src/utils.jl:289-302,
+src/lookup.jl:247-258, 374-389, and `Slicer`/`Indexer`/`IndexerView` of src/utils.jl:50-63,
 519-577.  Flux.Descent is mirrored by `Descent` (only `eta` is used, src/sparseupdate.jl:173).
 """
 from __future__ import annotations
@@ -90,7 +90,7 @@ class AbstractIndexer:
 
 
 class Indexer(AbstractIndexer):
-    """Caller-owned, reusable scratch for index! (reference src/utils.jl:527-543).  On the GPU it
+    """Caller-owned, reusable scratch for index! (reference src/utils.jl:288-304).  On the GPU it
     is a workspace in HBM holding the sorted (row, delta column) pairs and the bucket offsets
     (include/embtab_b200.h, etb_index_view).  It grows on demand and is then reused."""
 
@@ -129,12 +129,12 @@ class Indexer(AbstractIndexer):
         return out
 
 
-SparseIndexer = Indexer  # reference src/utils.jl:534-535: histogram flavours of the CPU algorithm;
+SparseIndexer = Indexer  # reference src/utils.jl:295-296: histogram flavours of the CPU algorithm;
 DenseIndexer = Indexer   # the GPU sort has one flavour
 
 
 class IndexerView(AbstractIndexer):
-    """IndexerView(I, num_splits, this_split) (reference src/utils.jl:559-572): a sub-range of the
+    """IndexerView(I, num_splits, this_split) (reference src/utils.jl:320-333): a sub-range of the
     buckets, for partitioned updates."""
 
     def __init__(self, I: Indexer, num_splits: int, this_split: int):
@@ -302,7 +302,7 @@ def ensemble_update(nthreads: int):
 # ------------------------------------------------------------------------------ pullbacks
 class Slicer:
     """Slicer(current_index, concat_dim, array): successive row-slice views of the concatenated
-    cotangent (reference src/utils.jl:289-302).  The reference's call operator increments a local
+    cotangent (reference src/utils.jl:50-63).  The reference's call operator increments a local
     copy of `current_index`, so it never advances; its own test (test/map.jl:153-177) requires
     per-table slices, which is what this implements.  concat_dim is 1 (rows)."""
 

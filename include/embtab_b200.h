@@ -29,7 +29,7 @@
  *   - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*).
  *   - the library never frees or retains caller memory; workspaces are
  *     caller-owned after a *_workspace_bytes query (the GPU analogue of the
- *     reference's caller-owned `Indexer`, src/utils.jl:527-543).
+ *     reference's caller-owned `Indexer`, src/utils.jl:288-304).
  */
 #ifndef EMBTAB_B200_H
 #define EMBTAB_B200_H
@@ -155,7 +155,7 @@ int32_t etb_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stre
 int32_t etb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
 /* Strided (2-D) copies: `height` runs of `width_bytes` contiguous bytes, run k at base + k * pitch.  This is the
  * row-slice view of a column-major matrix -- e.g. one table's rows of the concatenated cotangent
- * (reference src/utils.jl:289-302 Slicer, src/lookup.jl:374-389) -- moved without staging. */
+ * (reference src/utils.jl:50-63 Slicer, src/lookup.jl:374-389) -- moved without staging. */
 int32_t etb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes,
                          size_t height, void* stream);
 int32_t etb_memcpy2d_d2h(void* dst_host, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
@@ -191,13 +191,13 @@ int32_t etb_last_launch_count(void);
 /* K4. Group the occurrences of each distinct (table, row) of an ensemble, stable in
  * occurrence order (column-major traversal of the index matrix; the delta column of flat
  * position p is p / bag).  Replaces index!(indexer, indices, nrows) = histogram! +
- * prefixsum! + remap!, reference src/utils.jl:370-553, for all tables of an ensemble at once
+ * prefixsum! + remap!, reference src/utils.jl:131-314, for all tables of an ensemble at once
  * (reference src/sparseupdate.jl:211-213).  Buckets come out in ascending (table, row) order
  * instead of first-seen order; bucket members keep the reference's order.
  *
  * The result is described by an etb_index_view (a host POD of device pointers into the
  * caller's workspace -- the GPU analogue of the Indexer's `cumulative` and `map` fields,
- * reference src/utils.jl:527-532):
+ * reference src/utils.jl:288-293):
  *   keys[n_total]  sorted composite keys (table_slot << row_bits | row-1), uint32 or uint64
  *   map[n_total]   delta column (0-based) of each sorted position        (reference `map`)
  *   records[nnz]   one etb_bucket_record per bucket                      (reference `cumulative`)
@@ -219,7 +219,7 @@ typedef struct etb_index_view {
     int64_t n_total;        /* sum of occurrences over items */
     int32_t key_bytes;      /* 4 or 8 */
     int32_t row_bits;       /* key = slot << row_bits | (row-1) */
-    /* IndexerView(indexer, num_splits, this_split), reference src/utils.jl:559-577: restrict an
+    /* IndexerView(indexer, num_splits, this_split), reference src/utils.jl:320-338: restrict an
      * update to buckets (this_split-1)*s .. min(this_split*s, nnz)-1 with s = cdiv(nnz+1,
      * num_splits).  num_splits == 0 (what etb_index writes) = all buckets. */
     int32_t num_splits;
@@ -303,6 +303,21 @@ int32_t etb_ipc_close(void* ptr);
 int32_t etb_a2a_scatter(void* const* dst_ptrs_host, const void* src, int64_t ld_src,
                         const int64_t* rows_host, const int64_t* row_off_host, int32_t nranks,
                         int64_t batch_local, int32_t elt, void* stream);
+
+/* etb_a2a_scatter with a leading dimension per destination: block r lands as a rows_host[r] x batch_local matrix
+ * whose columns are dst_ld_host[r] elements apart -- a row block INSIDE the owner's cotangent buffer, so the backward
+ * exchange can run table group by table group while the owner already updates the groups that have arrived. */
+int32_t etb_a2a_scatter_ld(void* const* dst_ptrs_host, const int64_t* dst_ld_host, const void* src, int64_t ld_src,
+                           const int64_t* rows_host, const int64_t* row_off_host, int32_t nranks,
+                           int64_t batch_local, int32_t elt, void* stream);
+
+/* Stream-ordered barrier over peer memory (no collective library call): flag_ptrs_host[r] is rank r's flag array
+ * (nranks zero-initialised uint32, allocated with etb_malloc by r and mapped here with etb_ipc_import; my own entry
+ * is my local array).  One tiny kernel stores `epoch` into slot `rank` of every rank's array with release
+ * semantics at system scope and spins until all slots of my own array have reached `epoch`.  Kernels enqueued before
+ * it on `stream` are complete when it signals, so their peer stores are visible to every rank that passes the
+ * barrier.  `epoch` must grow by one per barrier (wrap-around is handled).  Every rank must call it. */
+int32_t etb_peer_barrier(void* const* flag_ptrs_host, int32_t rank, int32_t nranks, uint32_t epoch, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

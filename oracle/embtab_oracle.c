@@ -24,6 +24,7 @@
 #include <immintrin.h>
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdatomic.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -65,6 +66,67 @@ static int has_avx512(void) {
 /* tests force the portable loops so both code paths are compared with each other */
 void etbo_force_portable(int on) { g_has_avx512 = on ? 0 : (__builtin_cpu_supports("avx512f") ? 1 : 0); }
 int etbo_uses_avx512(void) { return has_avx512(); }
+
+/* ---------------------------------------------------------------------------------------
+ * Benchmark support (bench.py's CPU arm): one worker thread per core, pinned -- the state
+ * Polyester's `@batch per=thread` loops run in with JULIA_NUM_THREADS = cores and pinned
+ * threads -- and a threaded fill for the 13 GB of synthetic tables.
+ * ------------------------------------------------------------------------------------- */
+static int g_pin_threads = 0;
+void etbo_set_pinning(int on) { g_pin_threads = on; }
+
+/* number of CPUs this process may run on (the honest `cores` of the baseline) */
+int etbo_allowed_cpus(void) {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) != 0) return 1;
+    int n = CPU_COUNT(&set);
+    return n > 0 ? n : 1;
+}
+
+static void pin_worker(int tid) {
+    if (!g_pin_threads) return;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) != 0) return;
+    int n = CPU_COUNT(&set);
+    if (n <= 0) return;
+    int want = tid % n, seen = 0;
+    for (int c = 0; c < CPU_SETSIZE; ++c) {
+        if (!CPU_ISSET(c, &set)) continue;
+        if (seen++ == want) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(c, &one);
+            pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+            return;
+        }
+    }
+}
+
+typedef struct { float* dst; size_t n; uint64_t seed; int tid; } fill_job;
+static void* fill_worker(void* p) {
+    fill_job* j = (fill_job*)p;
+    pin_worker(j->tid);
+    uint64_t x = j->seed * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull * (uint64_t)(j->tid + 1);
+    for (size_t i = 0; i < j->n; ++i) { /* xorshift64*: uniform [0, 1) with 24 random bits, like rand(Float32) */
+        x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+        j->dst[i] = (float)((x * 0x2545F4914F6CDD1Dull) >> 40) * (1.0f / 16777216.0f);
+    }
+    return NULL;
+}
+void etbo_fill_uniform(float* dst, size_t n, uint64_t seed, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * nthreads);
+    fill_job* jobs = (fill_job*)malloc(sizeof(fill_job) * nthreads);
+    size_t per = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        size_t lo = (size_t)t * per, hi = lo + per < n ? lo + per : n;
+        jobs[t] = (fill_job){dst + (lo < n ? lo : n), lo < n ? hi - lo : 0, seed, t};
+        pthread_create(&th[t], NULL, fill_worker, &jobs[t]);
+    }
+    for (int t = 0; t < nthreads; ++t) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
 
 /* ---------------------------------------------------------------------------------------
  * Non-reducing lookup.  lookup_generic!(dst, src, indices::AbstractVector) src/lookup.jl:51-67
@@ -195,6 +257,7 @@ typedef struct {
 
 static void* map_worker(void* p) {
     map_job* job = (map_job*)p;
+    if (job->nthreads > 1) pin_worker(job->tid);
     if (job->strategy == 1) { /* static split of tables across threads */
         int per = (job->n_items + job->nthreads - 1) / job->nthreads;
         int lo = job->tid * per, hi = lo + per < job->n_items ? lo + per : job->n_items;
@@ -240,15 +303,15 @@ void etbo_maplookup(const etbo_lookup_item* items, int n_items, int strategy, in
 }
 
 /* ---------------------------------------------------------------------------------------
- * Indexer.  index!(I, A, maxindex) src/utils.jl:545-553 = histogram! + prefixsum! + remap!.
+ * Indexer.  index!(I, A, maxindex) src/utils.jl:306-314 = histogram! + prefixsum! + remap!.
  *
- * Traversal order of A is `columns(A)` (src/utils.jl:312-320): a vector yields (i, A[i]); a
+ * Traversal order of A is `columns(A)` (src/utils.jl:73-81): a vector yields (i, A[i]); a
  * matrix is walked column-major and yields (column, A[row, column]) -- i.e. flat position p
  * (0-based) belongs to delta column p / bag (+1).
  *
- * Dense variant (DenseIndexer, src/utils.jl:393-406, 429-478, 498-511): histogram is an array
+ * Dense variant (DenseIndexer, src/utils.jl:154-167, 190-239, 259-272): histogram is an array
  * of (order, count) over 1..maxindex.  Sparse variant (SparseIndexer: a Dictionaries.jl
- * insertion-ordered hash, src/utils.jl:375-391, 409-427, 481-496): restated with an
+ * insertion-ordered hash, src/utils.jl:136-152, 170-188, 242-257): restated with an
  * open-addressing table that records first-seen order, which is all the algorithm uses of it.
  *
  * Outputs (1-based, like the Julia structs): cum_col[nnz+1], cum_off[nnz+1] =
@@ -339,7 +402,7 @@ int64_t etbo_index_sparse(const int64_t* A, int64_t n, int64_t bag, int64_t maxi
     return nnz;
 }
 
-/* IndexerView(I, num_splits, this_split), src/utils.jl:564-572: range over `cumulative`
+/* IndexerView(I, num_splits, this_split), src/utils.jl:325-333: range over `cumulative`
  * (length nnz+1 incl. terminator).  Returns 1-based [start, stop]; entries processed by
  * update! are start .. stop-1 (the loop is over length(cumulative)-1, sparseupdate.jl:69,110). */
 void etbo_indexer_view(int64_t cum_len, int64_t num_splits, int64_t this_split, int64_t* start,
@@ -470,7 +533,7 @@ typedef struct etbo_update_item {
     const int64_t* idx;
     int64_t batch;
     int64_t bag; /* 0 = vector */
-    int64_t ld_idx; /* must equal bag (indices are traversed flat, utils.jl:315-320) */
+    int64_t ld_idx; /* must equal bag (indices are traversed flat, utils.jl:76-81) */
     /* caller-owned Indexer storage: cum_col/cum_off have n+1 slots, map has n */
     int64_t* cum_col;
     int64_t* cum_off;
@@ -487,6 +550,7 @@ typedef struct {
 
 static void* upd_worker(void* p) {
     upd_job* job = (upd_job*)p;
+    if (job->nthreads > 1) pin_worker(job->tid);
     if (job->phase == 1) {
         int per = (job->n_items + job->nthreads - 1) / job->nthreads;
         int lo = job->tid * per, hi = lo + per < job->n_items ? lo + per : job->n_items;

@@ -66,6 +66,7 @@ def lib():
         _lib.etbo_index_dense.restype = C.c_int64
         _lib.etbo_index_sparse.restype = C.c_int64
         _lib.etbo_uses_avx512.restype = C.c_int
+        _lib.etbo_allowed_cpus.restype = C.c_int
     return _lib
 
 
@@ -193,7 +194,7 @@ def maplookup(strategy: str, tables, I, prependrows=0, nthreads=1, worksize_div=
 
 
 def histogram_dense(A, maxindex):
-    """histogram!(array, A), reference src/utils.jl:370-373,393-406 -> (order[], count[])."""
+    """histogram!(array, A), reference src/utils.jl:131-134,154-167 -> (order[], count[])."""
     A = _idx(A).ravel(order="F")
     order = np.zeros(maxindex, np.int64)
     count = np.zeros(maxindex, np.int64)
@@ -203,7 +204,7 @@ def histogram_dense(A, maxindex):
 
 
 def index(A, maxindex, dense=False):
-    """index!(Indexer, A, maxindex), reference src/utils.jl:545-553.
+    """index!(Indexer, A, maxindex), reference src/utils.jl:306-314.
     Returns (cumulative, map): cumulative = list of (col, offset) incl. terminator, 1-based."""
     A = _idx(A)
     bag = 0 if A.ndim == 1 else A.shape[0]
@@ -274,6 +275,22 @@ def update_ensemble(tables, deltas, Is, eta, num_splits=4, nthreads=1, dense=Fal
     lib().etbo_update_ensemble(items, C.c_int(n), C.c_double(eta), C.c_int(num_splits),
                                C.c_int(nthreads), C.c_int(int(dense)))
     return scratch
+
+
+def set_pinning(on: bool):
+    """bench.py's CPU arm: pin worker thread t to the t-th CPU this process may run on"""
+    lib().etbo_set_pinning(C.c_int(int(on)))
+
+
+def allowed_cpus() -> int:
+    return int(lib().etbo_allowed_cpus())
+
+
+def fill_uniform(a: np.ndarray, seed: int, nthreads: int):
+    """threaded uniform [0, 1) Float32 fill (synthetic tables of the CPU arm; first touch by pinned threads)"""
+    assert a.dtype == np.float32 and (a.flags.f_contiguous or a.flags.c_contiguous)
+    lib().etbo_fill_uniform(C.c_void_p(a.ctypes.data), C.c_size_t(a.size), C.c_uint64(seed), C.c_int(nthreads))
+    return a
 
 
 def alloc_indexers(Is):

@@ -1,5 +1,6 @@
-"""Run under torchrun (or with RANK/WORLD_SIZE=0/1): sharded forward/backward/update vs the
-single-GPU path recomputed locally on every rank, bit for bit."""
+"""Run under torchrun (or with RANK/WORLD_SIZE=0/1): sharded forward/backward/update vs the CPU ORACLE and vs the
+single-GPU path recomputed locally on every rank, bit for bit -- NCCL all-to-all, fused NVLink peer stores with
+the NCCL barrier, and fused with the peer-memory flag barrier and the table-group pipelined backward."""
 import os
 import sys
 
@@ -8,9 +9,10 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (ROOT, os.path.join(ROOT, "embeddingtables.jl_b200")):
+for p in (ROOT, os.path.join(ROOT, "embeddingtables.jl_b200"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 import embtab as E
+import oracle as O          # the checker (tests/ may use it)
 from embtab.dist import ShardedEnsemble, ShardPlan
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -33,24 +35,41 @@ ref_tables = [make_table(t) for t in range(len(base))]
 ref_out, back = E.pullback(E.maplookup, E.PreallocationStrategy(prepend), ref_tables, I)
 E.update_(E.Descent(0.1), ref_tables, back(delta)[2], [E.Indexer()])
 
+# ... and the oracle: the single-GPU path equals it, so the sharded path (compared with both below) does too
+orc = [O.Table(base[t].copy(order="F"), static=bool(t % 2), cols_per_shard=200 if t % 2 else None) for t in range(len(base))]
+orc_out = O.maplookup("preallocation", orc, I, prependrows=prepend, out=np.zeros((total, batch), np.float32, order="F"))
+off, deltas = prepend, []
+for d in dims:
+    deltas.append(np.asfortranarray(delta[off:off + d]))
+    off += d
+O.update_ensemble(orc, deltas, I, 0.1)
+assert np.array_equal(ref_out.numpy()[prepend:], orc_out[prepend:]), "single-GPU forward differs from the oracle"
+for t in range(len(base)):
+    assert np.array_equal(ref_tables[t].to_numpy(), orc[t].dense()), f"single-GPU update of table {t} differs from the oracle"
+
 plan = ShardPlan(dims, world, rank, prepend, batch)
 mine = list(plan.my_tables)
-for fused in (False, True):     # NCCL all-to-all + pack/unpack, then NVLink peer stores
-    ens = ShardedEnsemble([make_table(t) for t in mine], plan, fused=fused)
+# NCCL all-to-all + pack/unpack; NVLink peer stores + NCCL barrier; peer stores + flag barrier + pipelined backward
+for fused, groups, peer_barrier in ((False, 1, False), (True, 1, False), (True, 3, True)):
+    ens = ShardedEnsemble([make_table(t) for t in mine], plan, fused=fused, table_groups=groups, peer_barrier=peer_barrier)
     ens.out.fill(-5.0)
     torch.cuda.synchronize()
     dist.barrier()
     for rep in range(2):        # twice: buffers are reused across steps
         out = ens.forward([I[t] for t in mine])
         got = out.numpy()
-        want = ref_out.numpy()[:, plan.clo[rank]:plan.chi[rank]]
-        assert np.array_equal(got[prepend:], want[prepend:]), f"sharded forward differs (fused={fused})"
+        want = orc_out[:, plan.clo[rank]:plan.chi[rank]]
+        assert np.array_equal(got[prepend:], want[prepend:]), f"sharded forward differs from the oracle (fused={fused})"
         assert np.all(got[:prepend] == -5.0), "prepend rows were touched"
         d_local = E.DeviceArray.from_numpy(delta[:, plan.clo[rank]:plan.chi[rank]])
-        grads = ens.backward(d_local)
-        if rep == 1:            # update once, after the second (buffer-reusing) round trip
-            ens.update_(E.Descent(0.1), grads)
+        if rep == 0:
+            grads = ens.backward(d_local)
+        elif groups > 1:        # update once, after the second (buffer-reusing) round trip: group by group
+            ens.backward_update_(E.Descent(0.1), d_local)
+        else:
+            ens.update_(E.Descent(0.1), ens.backward(d_local))
     for t, tab in zip(mine, ens.tables):
+        assert np.array_equal(tab.to_numpy(), orc[t].dense()), f"table {t} differs from the oracle after update (fused={fused}, groups={groups})"
         assert np.array_equal(tab.to_numpy(), ref_tables[t].to_numpy()), f"table {t} differs after update (fused={fused})"
     torch.cuda.synchronize()
     dist.barrier()
@@ -67,5 +86,5 @@ for wire in (None, np.int32):
 torch.cuda.synchronize()
 dist.barrier()
 if rank == 0:
-    print("dist check ok", world)
+    print("dist check ok", world, "(sharded == single GPU == oracle, bit for bit: NCCL, fused + NCCL barrier, fused + peer-flag barrier + grouped backward)")
 dist.destroy_process_group()

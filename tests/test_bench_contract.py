@@ -1,5 +1,7 @@
 """CPU check of bench.py's contract for the reference arm (the GPU arm needs a B200): one JSON line with the
-keys the driver reads, produced by the CPU port of the reference on a bounded sample."""
+keys the driver reads, produced by the CPU port of the reference on the FULL ensemble of the workload (the reference's
+index! phase is table-parallel only, so a sample of a few tables would starve the host cores), for exactly the
+steps / warm-up the driver asks for, with the same `config` dict the GPU arm emits."""
 import json
 import os
 import subprocess
@@ -9,17 +11,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "embedding_lookups_per_sec" and d["unit"] == "lookups/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
-    assert d["config"]["workload"].startswith("C2")
+    assert d["steps"] == 2 and d["warmup"] == 1                      # what the driver passed, not a clamp
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.common_config(1, "uniform")          # the dict the GPU arm emits too
+    assert d["config"]["workload"].startswith("C2") and d["config"]["tables"] == 26
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == os.cpu_count() and cb["value"] == d["value"] and "sample" in cb
+    assert cb["kind"] == "port" and cb["cores"] == len(os.sched_getaffinity(0)) and cb["value"] == d["value"]
+    assert cb["sample"].startswith("all 26 tables") and "pinned" in cb["sample"]   # the full ensemble, not a sample of it
     assert d["e2e"] == {"value": d["value"], "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

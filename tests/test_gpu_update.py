@@ -406,7 +406,7 @@ def test_wide_keys_path(E, O):
 @pytest.mark.parametrize("n,nrows,wide", [(1_000_003, 5000, False), (300_000, 70_000_000, False), (200_000, 9000, True), (77, 50, False)])
 def test_index_sort_is_a_stable_sort(E, n, nrows, wide):
     # the hand-written radix sort behind index!: sorted by row, and STABLE -- members of a bucket keep the
-    # occurrence order (what remap! records, reference src/utils.jl:481-511); checked against numpy's stable sort
+    # occurrence order (what remap! records, reference src/utils.jl:242-272); checked against numpy's stable sort
     from embtab.sparseupdate import _IndicesOnly, _peek
 
     class Declared(E.SimpleEmbedding):          # only the declared row count matters to index!
