@@ -197,8 +197,40 @@ int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int3
             P.tile0 = (uint32_t)tile0;
             tile0 += rt;
         }
+        const bool rec_inline = L.rec_tiles <= 2048;  // few record tiles: no scan kernel
+        // small tables (every table at most one tile): one CTA sorts a table in shared memory, all passes at once
+        int64_t max_n = 0;
+        for (int i = 0; i < n_items; ++i) max_n = std::max<int64_t>(max_n, items[i].batch * (items[i].bag ? items[i].bag : 1));
+        const bool small = max_n <= kIxTile && L.key_bytes == 4;
         for (IxParams& P : groups) {
+            P.rec_inline = rec_inline;
+            P.rec_total = (int32_t)L.rec_tiles;
             if (P.ntiles == 0) continue;
+            if (small) {
+                P.pass = 0;
+                P.kin = nullptr;
+                P.vin = nullptr;
+                P.kout = keys[fin];
+                P.vout = vals[fin];
+                const size_t smem = ix_small_smem<uint32_t>(L.nb_max);
+                const int rank = ix_rank_mode();
+#define ETB_SMALL(SRC, RK)                                                                                                 \
+    do {                                                                                                                   \
+        static thread_local size_t configured = 0;                                                                         \
+        if (smem > configured) {                                                                                           \
+            ETB_CUDA(cudaFuncSetAttribute(ix_small_kernel<uint32_t, SRC, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            configured = smem;                                                                                             \
+        }                                                                                                                  \
+        ix_small_kernel<uint32_t, SRC, RK><<<P.n_items, kIxThreads, smem, stream>>>(P, L.npasses);                         \
+    } while (0)
+                if (idx_elt == ETB_I64) { if (rank) ETB_SMALL(long long, 1); else ETB_SMALL(long long, 0); }
+                else { if (rank) ETB_SMALL(int, 1); else ETB_SMALL(int, 0); }
+#undef ETB_SMALL
+                ETB_LAUNCHED();
+                P.kin = keys[fin];
+                P.vin = vals[fin];
+                continue;
+            }
             // K4a: the partition passes, least significant digit first; pass q reads buffer (q - 1) & 1 (the first one
             // reads the index arrays) and writes buffer q & 1
             for (int q = 0; q < L.npasses; ++q) {
@@ -218,8 +250,10 @@ int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int3
             else ix_count_heads_kernel<uint64_t><<<P.rec_tiles, kIxThreads, 0, stream>>>(P);
             ETB_LAUNCHED();
         }
-        ix_scan_counts_kernel<<<1, 1024, 0, stream>>>((uint32_t*)(base + L.off_rec_counts), (int)L.rec_tiles, nnz);
-        ETB_LAUNCHED();
+        if (!rec_inline) {
+            ix_scan_counts_kernel<<<1, 1024, 0, stream>>>((uint32_t*)(base + L.off_rec_counts), (int)L.rec_tiles, nnz);
+            ETB_LAUNCHED();
+        }
         for (IxParams& P : groups) {  // one record per bucket head, numbered over the whole call
             if (P.ntiles == 0) continue;
             if (L.key_bytes == 4) ix_write_records_kernel<uint32_t><<<P.rec_tiles, kIxThreads, 0, stream>>>(P);

@@ -54,7 +54,9 @@ struct IxParams {
     uint32_t* digit_total;  // [n_items][nb]
     BucketRec* recs;
     int64_t* nnz;
-    uint32_t* rec_counts;   // [tiles of the call + 1] bucket heads per tile, then exclusive offsets
+    uint32_t* rec_counts;   // [tiles of the call + 1] bucket heads per tile, then exclusive offsets (rec_inline: counts)
+    int32_t rec_inline;     // few tiles: ix_write_records_kernel adds up the counts before its tile itself (no scan kernel)
+    int32_t rec_total;      // record tiles of the whole call
     int32_t n_items, ntiles, rec_tiles, pass, slot0, row_bits;
     uint32_t tile0;         // record tiles of the earlier launches of this call
     uint8_t width[8], shift[8];
@@ -228,44 +230,17 @@ static __device__ __noinline__ uint32_t ix_rank_shared_digit(uint32_t d, bool va
     return now - __popc(peers) + __popc(peers & ((1u << lane) - 1u));
 }
 
-// RANK = 0: peer masks from one ballot per digit bit for every row, per-warp counters updated by the leader of each
-// peer group.  RANK = 1: shared-memory atomics on the per-warp counters; ballots only for rows in which two lanes
-// share a digit.  (Both are stable; which one is faster is a measurement, ETB_IX_RANK selects.)
-template <typename KeyT, typename SrcT, int RANK, int THREADS>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) ix_scatter_kernel(const __grid_constant__ IxParams P) {
-    constexpr bool kFirst = !std::is_void<SrcT>::value;
-    constexpr int kIxThreads = THREADS, kIxWarps = THREADS / 32, kIxTile = THREADS * kIxItems;  // shadow the record kernels' constants
-    constexpr int kIxMaxBpt = kIxMaxBins / THREADS;  // digits per thread in the per-digit steps
-    extern __shared__ __align__(16) unsigned char ix_smem[];
-    const int nbits = P.width[P.pass], shift = P.shift[P.pass];
-    const int nb = 1 << nbits;
-    const uint32_t dmask = (uint32_t)nb - 1u;
-    const int bpt = max(1, nb / kIxThreads);  // digits per thread: d = tid * bpt + j
-    IxPair<KeyT>* spair = (IxPair<KeyT>*)ix_smem;
-    uint16_t* wcount = (uint16_t*)(spair + kIxTile);                 // [kIxWarps][nb]
-    uint32_t* tstart = (uint32_t*)(wcount + (size_t)kIxWarps * nb);  // [nb] tile-local start of each digit; after the
-    uint32_t* gbase = tstart;                                        // reorder: output position of that start, minus it
-    uint32_t* warp_tot = tstart + nb;                                // [2 * kIxWarps]
-
+// Stable rank of every element of a tile among the equal digits of its warp.  Warp w owns positions
+// [w * 32 * kIxItems, ...), 32 consecutive ones per step (element i of lane l = position w*512 + i*32 + l), so ranks
+// follow position order.  wcount: [warps][nb] 16-bit counters, zero on entry; on exit the per-warp digit counts.
+// RANK = 0: peer masks from one ballot per digit bit for every row, counters updated by the leader of each peer
+// group.  RANK = 1: shared-memory atomics on the counters; ballots only for rows in which two lanes share a digit.
+// (Both are stable; which one is faster is a measurement, ETB_IX_RANK selects.)  rk: two 16-bit ranks per register.
+template <typename KeyT, int RANK>
+__device__ __forceinline__ void ix_rank_rows(const KeyT (&k)[kIxItems], uint32_t (&rk)[kIxItems / 2], uint16_t* wcount, int nb,
+                                             int nbits, int shift, int tile_n) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < kIxWarps * nb / 2; i += kIxThreads) ((uint32_t*)wcount)[i] = 0;
-    const int item = ix_find_item<false>(P, blockIdx.x);
-    const IxItem& it = P.item[item];
-    const uint32_t tbase = (blockIdx.x - it.tile_start) * kIxTile;  // first position of the tile in the table's segment
-    const int tile_n = (int)min((uint32_t)kIxTile, it.n - tbase);
-    const KeyT* kin = (const KeyT*)P.kin + it.seg_start;
-    const int32_t* vin = P.vin + it.seg_start;
-    // ---- keys of the tile, all loads first.  Warp w owns positions [w * 512, (w + 1) * 512), 32 consecutive ones per
-    // step, so ranks follow position order.
-    KeyT k[kIxItems];
-#pragma unroll
-    for (int i = 0; i < kIxItems; ++i) {
-        const int q = warp * (32 * kIxItems) + i * 32 + lane;
-        k[i] = ix_load_key<KeyT, SrcT>(it, kin, tbase + min(q, tile_n - 1));
-    }
-    __syncthreads();
-    // ---- stable rank of every element among the equal digits of its warp
-    uint32_t rk[kIxItems / 2];  // two 16-bit ranks per register
+    const uint32_t dmask = (uint32_t)nb - 1u;
     if constexpr (RANK == 1) {
         uint32_t* cw = (uint32_t*)(wcount + (size_t)warp * nb);  // two 16-bit counters per word
 #pragma unroll
@@ -313,6 +288,44 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) ix_scatter_ke
             __syncwarp();
         }
     }
+}
+
+template <typename KeyT, typename SrcT, int RANK, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) ix_scatter_kernel(const __grid_constant__ IxParams P) {
+    constexpr bool kFirst = !std::is_void<SrcT>::value;
+    constexpr int kIxThreads = THREADS, kIxWarps = THREADS / 32, kIxTile = THREADS * kIxItems;  // shadow the record kernels' constants
+    constexpr int kIxMaxBpt = kIxMaxBins / THREADS;  // digits per thread in the per-digit steps
+    extern __shared__ __align__(16) unsigned char ix_smem[];
+    const int nbits = P.width[P.pass], shift = P.shift[P.pass];
+    const int nb = 1 << nbits;
+    const uint32_t dmask = (uint32_t)nb - 1u;
+    const int bpt = max(1, nb / kIxThreads);  // digits per thread: d = tid * bpt + j
+    IxPair<KeyT>* spair = (IxPair<KeyT>*)ix_smem;
+    uint16_t* wcount = (uint16_t*)(spair + kIxTile);                 // [kIxWarps][nb]
+    uint32_t* tstart = (uint32_t*)(wcount + (size_t)kIxWarps * nb);  // [nb] tile-local start of each digit; after the
+    uint32_t* gbase = tstart;                                        // reorder: output position of that start, minus it
+    uint32_t* warp_tot = tstart + nb;                                // [2 * kIxWarps]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kIxWarps * nb / 2; i += kIxThreads) ((uint32_t*)wcount)[i] = 0;
+    const int item = ix_find_item<false>(P, blockIdx.x);
+    const IxItem& it = P.item[item];
+    const uint32_t tbase = (blockIdx.x - it.tile_start) * kIxTile;  // first position of the tile in the table's segment
+    const int tile_n = (int)min((uint32_t)kIxTile, it.n - tbase);
+    const KeyT* kin = (const KeyT*)P.kin + it.seg_start;
+    const int32_t* vin = P.vin + it.seg_start;
+    // ---- keys of the tile, all loads first.  Warp w owns positions [w * 512, (w + 1) * 512), 32 consecutive ones per
+    // step, so ranks follow position order.
+    KeyT k[kIxItems];
+#pragma unroll
+    for (int i = 0; i < kIxItems; ++i) {
+        const int q = warp * (32 * kIxItems) + i * 32 + lane;
+        k[i] = ix_load_key<KeyT, SrcT>(it, kin, tbase + min(q, tile_n - 1));
+    }
+    __syncthreads();
+    // ---- stable rank of every element among the equal digits of its warp
+    uint32_t rk[kIxItems / 2];  // two 16-bit ranks per register
+    ix_rank_rows<KeyT, RANK>(k, rk, wcount, nb, nbits, shift, tile_n);
     __syncthreads();
     // ---- per digit: exclusive prefix over the warps (in place), the tile's count; tile-local digit starts and the
     // table's digit bases (two block scans sharing their barriers).  The write-out bases stay in registers until the
@@ -399,20 +412,137 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) ix_scatter_ke
     }
 }
 
+// ------------------------------------------------------------------------------------ small tables
+// Every table of the launch has at most one tile (4096 occurrences): one CTA sorts a whole table in shared memory --
+// all passes back to back, no histogram / scan kernels, nothing but the sorted pairs and the head count goes to
+// global memory.  C1 (26 tables x 2048 indices) is 2 launches this way instead of 9.
+template <typename KeyT>
+constexpr size_t ix_small_smem(int nb) {
+    return (size_t)kIxTile * sizeof(IxPair<KeyT>) + (size_t)kIxWarps * nb * sizeof(uint16_t) + (size_t)nb * sizeof(uint32_t) +
+           2 * kIxWarps * sizeof(uint32_t);
+}
+
+template <typename KeyT, typename SrcT, int RANK>
+__global__ void __launch_bounds__(kIxThreads) ix_small_kernel(const __grid_constant__ IxParams P, int npasses) {
+    constexpr int kMaxBpt = kIxMaxBins / kIxThreads;
+    extern __shared__ __align__(16) unsigned char ix_smem[];
+    const int nb_max = 1 << P.width[0];
+    IxPair<KeyT>* spair = (IxPair<KeyT>*)ix_smem;
+    uint16_t* wcount = (uint16_t*)(spair + kIxTile);                     // [kIxWarps][nb]
+    uint32_t* tstart = (uint32_t*)(wcount + (size_t)kIxWarps * nb_max);  // [nb]
+    uint32_t* warp_tot = tstart + nb_max;                                // [2 * kIxWarps]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const IxItem& it = P.item[blockIdx.x];
+    const int tile_n = (int)it.n;
+    if (tile_n == 0) return;
+    KeyT k[kIxItems];
+    int32_t v[kIxItems];
+#pragma unroll
+    for (int i = 0; i < kIxItems; ++i) {  // element i of lane l = position w*512 + i*32 + l
+        const int q = min(warp * (32 * kIxItems) + i * 32 + lane, tile_n - 1);
+        uint32_t col;
+        k[i] = (KeyT)((int64_t)__ldg((const SrcT*)it.idx + ix_src_pos(it, (uint32_t)q, &col)) - 1);
+        v[i] = (int32_t)col;
+    }
+    for (int pass = 0; pass < npasses; ++pass) {
+        const int nbits = P.width[pass], shift = P.shift[pass];
+        const int nb = 1 << nbits;
+        const uint32_t dmask = (uint32_t)nb - 1u;
+        const int bpt = max(1, nb / kIxThreads);
+        for (int i = threadIdx.x; i < kIxWarps * nb / 2; i += kIxThreads) ((uint32_t*)wcount)[i] = 0;
+        __syncthreads();
+        uint32_t rk[kIxItems / 2];
+        ix_rank_rows<KeyT, RANK>(k, rk, wcount, nb, nbits, shift, tile_n);
+        __syncthreads();
+        {   // per digit: exclusive prefix over the warps (in place) and the digit's start
+            uint32_t cnt[kMaxBpt], tsum = 0, dummy = 0;
+#pragma unroll
+            for (int j = 0; j < kMaxBpt; ++j) {
+                const int d = threadIdx.x * bpt + j;
+                uint32_t run = 0;
+                if (j < bpt && d < nb) {
+#pragma unroll
+                    for (int w = 0; w < kIxWarps; ++w) {
+                        const uint32_t c = wcount[w * nb + d];
+                        wcount[w * nb + d] = (uint16_t)run;
+                        run += c;
+                    }
+                }
+                cnt[j] = run;
+                tsum += run;
+            }
+            uint32_t ta, tb;
+            ix_block_exscan2<kIxThreads>(tsum, dummy, warp_tot, &ta, &tb);
+#pragma unroll
+            for (int j = 0; j < kMaxBpt; ++j) {
+                const int d = threadIdx.x * bpt + j;
+                if (j < bpt && d < nb) {
+                    tstart[d] = tsum;
+                    tsum += cnt[j];
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kIxItems; ++i) {
+            const int q = warp * (32 * kIxItems) + i * 32 + lane;
+            if (q < tile_n) {
+                const uint32_t d = (uint32_t)(k[i] >> shift) & dmask;
+                const uint32_t rank = (rk[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+                spair[tstart[d] + wcount[warp * nb + d] + rank] = IxPair<KeyT>{k[i], v[i]};
+            }
+        }
+        __syncthreads();
+        if (pass + 1 < npasses) {  // the next pass ranks the elements in their new order
+#pragma unroll
+            for (int i = 0; i < kIxItems; ++i) {
+                const IxPair<KeyT> pr = spair[min(warp * (32 * kIxItems) + i * 32 + lane, tile_n - 1)];
+                k[i] = pr.k;
+                v[i] = pr.v;
+            }
+        }
+    }
+    // sorted pairs out (coalesced) and the number of bucket heads of this table = its record tile
+    KeyT* kout = (KeyT*)P.kout + it.seg_start;
+    int32_t* vout = P.vout + it.seg_start;
+    uint32_t heads = 0;
+    for (int q = threadIdx.x; q < tile_n; q += kIxThreads) {
+        const IxPair<KeyT> pr = spair[q];
+        kout[q] = pr.k;
+        vout[q] = pr.v;
+        heads += (q == 0 || spair[q - 1].k != pr.k) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) heads += __shfl_xor_sync(0xffffffffu, heads, o);
+    __syncthreads();
+    if (lane == 0) warp_tot[warp] = heads;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+#pragma unroll
+        for (int w = 0; w < kIxWarps; ++w) t += warp_tot[w];
+        P.rec_counts[P.tile0 + it.rec_tile_start] = t;
+    }
+}
+
 // ------------------------------------------------------------------------------------ bucket records
 // Position p of a table's sorted segment is a bucket head when it is the segment's first position or its key
 // differs from the previous one.  Positions are striped over the block (p = base + i*256 + tid) so every load is
 // coalesced; ranks follow position order (i-major, then warp, then lane) via warp ballots.
 template <typename KeyT>
 __device__ __forceinline__ uint32_t ix_head_flags(const KeyT* __restrict__ keys, uint32_t base, uint32_t n, KeyT (&k)[kIxItems]) {
+    KeyT prev[kIxItems];
+#pragma unroll
+    for (int i = 0; i < kIxItems; ++i) {  // all loads first, unconditionally (positions past the end repeat the last one)
+        const uint32_t p = min(base + i * kIxThreads + threadIdx.x, n - 1);
+        k[i] = __ldg(keys + p);
+        prev[i] = __ldg(keys + (p ? p - 1 : 0));
+    }
     uint32_t flags = 0;
 #pragma unroll
     for (int i = 0; i < kIxItems; ++i) {
         const uint32_t p = base + i * kIxThreads + threadIdx.x;
-        if (p < n) {
-            k[i] = __ldg(keys + p);
-            if (p == 0 || __ldg(keys + p - 1) != k[i]) flags |= 1u << i;
-        }
+        if (p < n && (p == 0 || prev[i] != k[i])) flags |= 1u << i;
     }
     return flags;
 }
@@ -473,10 +603,19 @@ __global__ void __launch_bounds__(1024) ix_scan_counts_kernel(uint32_t* __restri
 template <typename KeyT>
 __global__ void __launch_bounds__(kIxThreads) ix_write_records_kernel(const __grid_constant__ IxParams P) {
     __shared__ uint32_t cnt[kIxItems][kIxWarps];  // heads per (item row, warp), then exclusive offsets
+    __shared__ uint32_t warp_sums[kIxWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = ix_find_item<true>(P, blockIdx.x);
     const IxItem& it = P.item[item];
     const uint32_t tbase = (blockIdx.x - it.rec_tile_start) * kIxTile;
+    const uint32_t gt = P.tile0 + blockIdx.x;  // tile number within the whole call
+    uint32_t off = 0;
+    if (P.rec_inline) {  // buckets before this tile
+        for (uint32_t j = threadIdx.x; j < gt; j += kIxThreads) off += P.rec_counts[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+        if (lane == 0) warp_sums[warp] = off;
+    }
     KeyT k[kIxItems];
     const uint32_t flags = ix_head_flags((const KeyT*)P.kin + it.seg_start, tbase, it.n, k);
     uint32_t before[kIxItems];  // heads of lower lanes in my warp, per item row
@@ -502,17 +641,32 @@ __global__ void __launch_bounds__(kIxThreads) ix_write_records_kernel(const __gr
         uint32_t run = incl - sum;
 #pragma unroll
         for (int j = 0; j < kPer; ++j) { flat[threadIdx.x * kPer + j] = run; run += v[j]; }
+        if (P.rec_inline && lane == 31 && gt == (uint32_t)P.rec_total - 1) {  // the last tile of the call: nnz
+            uint32_t before_me = 0;
+#pragma unroll
+            for (int w = 0; w < kIxWarps; ++w) before_me += warp_sums[w];
+            *P.nnz = (int64_t)(before_me + incl);
+        }
     }
     __syncthreads();
-    const uint32_t tile_off = P.rec_counts[P.tile0 + blockIdx.x];
+    uint32_t tile_off = 0;
+    if (P.rec_inline) {
+#pragma unroll
+        for (int w = 0; w < kIxWarps; ++w) tile_off += warp_sums[w];
+    } else {
+        tile_off = P.rec_counts[gt];
+    }
     const uint64_t slot = (uint64_t)(P.slot0 + item) << P.row_bits;
+    int32_t m0[kIxItems];
+#pragma unroll
+    for (int i = 0; i < kIxItems; ++i)  // the first member of every position, heads or not: 16 coalesced loads in flight
+        m0[i] = __ldg(P.vin + it.seg_start + min(tbase + i * kIxThreads + threadIdx.x, it.n - 1));
 #pragma unroll
     for (int i = 0; i < kIxItems; ++i) {
         if ((flags >> i) & 1u) {
-            const uint32_t p = it.seg_start + tbase + i * kIxThreads + threadIdx.x;
             BucketRec r;
-            r.start = p;
-            r.m0 = __ldg(P.vin + p);
+            r.start = it.seg_start + tbase + i * kIxThreads + threadIdx.x;
+            r.m0 = m0[i];
             r.key = slot | (uint64_t)k[i];
             P.recs[tile_off + cnt[i][warp] + before[i]] = r;
         }

@@ -67,6 +67,7 @@ struct UpdParams {
     int32_t slot0, nslots;  // this launch handles slots [slot0, slot0 + nslots)
     int32_t G, nvec;
     int32_t fma, split_long;
+    int32_t strict_long;  // strict order and the rows fit one pass: buckets of > kLongThreshold members go to long_strict_kernel
     int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:325-333
     // row-wise Adagrad only (OPT == kOptAdagrad): per-item state vectors (one acc_t element per table row)
     double eps;
@@ -201,6 +202,11 @@ __device__ __forceinline__ void accumulate_members(AccVec<T, VB> (&acc)[VPL], co
 // sized for the upper bound n_total and surplus warps exit.
 // hand a bucket to the long path: fixed-size chunks, combined in chunk order (cold; kept out of line
 // so that it costs the hot loop no registers)
+// strict order: a long bucket is one job of long_strict_kernel (one CTA streams its member rows through shared memory)
+__device__ __noinline__ void register_strict_long_bucket(LongCounters* counters, LongRec* longs, uint32_t bucket) {
+    longs[atomicAdd(&counters->n_long, 1u)] = LongRec{bucket, 0u, 0u, 0u};
+}
+
 __device__ __noinline__ void register_long_bucket(LongCounters* counters, LongRec* longs, ChunkRec* chunks,
                                                   uint32_t bucket, int cnt) {
     const uint32_t nch = (uint32_t)((cnt + kLongChunk - 1) / kLongChunk);
@@ -268,6 +274,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         int cnt = mine ? (int)(stop - start) : 0;
         if (cnt > kShortMax) {
             if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            else if (P.strict_long && cnt > kLongThreshold) register_strict_long_bucket(P.counters, P.longs, (uint32_t)s);
             else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
         }
@@ -399,6 +406,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         int cnt = mine ? (int)(stop - (int64_t)raw.x) : 0;
         if (cnt > kShortMax) {
             if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            else if (P.strict_long && cnt > kLongThreshold) register_strict_long_bucket(P.counters, P.longs, (uint32_t)s);
             else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
         }
@@ -669,6 +677,134 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
     }
 }
 
+// LONG buckets in STRICT order (the reference's: every member added one after the other, src/sparseupdate.jl:72-84,
+// 114-120).  The sum of one feature element is a serial chain of additions, so a hot row's time is members x (one
+// add); what a GPU can do is make sure the chain never waits for memory: one CTA per long bucket, all 8 warps stream
+// the member rows into shared memory with cp.async (4 stages of up to 64 rows), and the first G lanes add them from
+// there in order (C3's hottest row has 45 k members: measurements in profiles/README.md).
+constexpr int kStrictStageBytes = 24 * 1024, kStrictStages = 4, kStrictMaxRows = 48;  // 96 KB: two CTAs per SM
+constexpr int kStrictPieces = 6;  // VB-byte pieces per thread and batch (a batch has at most 6 * 256 of them)
+
+template <int VB>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if constexpr (VB == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    else if constexpr (VB == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+
+template <typename T, int VB, int VPL, int OPT>
+__global__ void __launch_bounds__(kUThreads)
+long_strict_kernel(const __grid_constant__ UpdParams P) {
+    using V = Vec<T, VB>;
+    using A = AccVec<T, VB>;
+    extern __shared__ __align__(16) char s_rows[];  // [kStrictStages][rows_per_stage][nvec * VB]
+    const int G = P.G, nvec = P.nvec;
+    const int row_bytes = nvec * VB;
+    const int rows_per_stage = min(min(kStrictMaxRows, kStrictStageBytes / row_bytes), kStrictPieces * kUThreads / nvec);
+    const int gl = threadIdx.x & (G - 1);
+    const bool consumer = threadIdx.x < G;  // group 0 = the first G lanes of warp 0
+    // my pieces of a batch: piece pc = tid + k * 256 is vector pv[k] of the batch's row pr[k] -- the same for every
+    // batch, so the divisions happen once per kernel
+    int pr[kStrictPieces], pv[kStrictPieces];
+#pragma unroll
+    for (int k = 0; k < kStrictPieces; ++k) {
+        const int pc = threadIdx.x + k * kUThreads;
+        pr[k] = pc / nvec;
+        pv[k] = pc - pr[k] * nvec;
+    }
+    const uint32_t n_long = P.counters->n_long;
+    const int64_t nnz = *P.nnz;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    const acc_t<T> eta = (acc_t<T>)P.eta;
+    for (uint32_t j = blockIdx.x; j < n_long; j += gridDim.x) {
+        const LongRec lr = P.longs[j];
+        const BucketRec rec = P.recs[lr.bucket];
+        const int64_t start = rec.start;
+        const int64_t stop = ((int64_t)lr.bucket + 1 < nnz) ? (int64_t)P.recs[lr.bucket + 1].start : P.n_total;
+        const int slot = (int)(rec.key >> P.row_bits) - P.slot0;
+        const UpdDesc& d = P.item[slot];
+        char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
+        const int nbatch = (int)((stop - start + rows_per_stage - 1) / rows_per_stage);
+        // all threads: member rows of batch b -> stage b % 3, one VB-byte piece per thread and step
+        auto issue = [&](int b) {
+            if (b < nbatch) {
+                const int64_t m0 = start + (int64_t)b * rows_per_stage;
+                const int rows = (int)min((int64_t)rows_per_stage, stop - m0);
+                char* stage = s_rows + (size_t)(b % kStrictStages) * rows_per_stage * row_bytes;
+                int32_t col[kStrictPieces];
+#pragma unroll
+                for (int k = 0; k < kStrictPieces; ++k)  // the delta columns of my pieces' members first (independent loads)
+                    col[k] = pr[k] < rows ? __ldg(P.map + m0 + pr[k]) : 0;
+#pragma unroll
+                for (int k = 0; k < kStrictPieces; ++k)
+                    if (pr[k] < rows)
+                        cp_async<VB>(stage + (size_t)pr[k] * row_bytes + pv[k] * VB,
+                                     d.delta + (int64_t)col[k] * d.ld_delta_bytes + pv[k] * VB);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");  // one group per batch, empty ones included
+        };
+        A acc[VPL];
+        V old[VPL];
+        acc_t<T> st_old = acc_t<T>(0);
+        acc_t<T>* state = nullptr;
+        bool on[VPL];
+#pragma unroll
+        for (int p = 0; p < VPL; ++p) {
+            acc_fill(acc[p], acc_t<T>(0));  // accum = zero, then += members in order
+            on[p] = consumer && gl + p * G < nvec;
+            if (on[p]) ld_plain<VB>(&old[p], row + (size_t)(gl + p * G) * VB);
+        }
+        if (OPT == kOptAdagrad && consumer) {
+            state = (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask);
+            st_old = *state;
+        }
+        issue(0);
+        issue(1);
+        issue(2);
+        for (int b = 0; b < nbatch; ++b) {
+            asm volatile("cp.async.wait_group 2;" ::: "memory");  // my pieces of batch b have landed
+            __syncthreads();                                      // everybody's have; stage (b + 3) % 4 is free again
+            issue(b + 3);
+            if (consumer) {
+                const int rows = (int)min((int64_t)rows_per_stage, stop - (start + (int64_t)b * rows_per_stage));
+                const char* stage = s_rows + (size_t)(b % kStrictStages) * rows_per_stage * row_bytes;
+                for (int r = 0; r < rows; ++r) {
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p) {
+                        if (on[p]) {
+                            const V v = *(const V*)(stage + (size_t)r * row_bytes + (size_t)(gl + p * G) * VB);
+                            acc_add(acc[p], v);
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (consumer) {
+            if constexpr (OPT == kOptSgd) {
+#pragma unroll
+                for (int p = 0; p < VPL; ++p) {
+                    if (on[p]) {
+                        V out;
+#pragma unroll
+                        for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_apply<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
+                        st_plain<VB>(row + (size_t)(gl + p * G) * VB, &out);
+                    }
+                }
+            } else {
+                V out[VPL];
+                adagrad_apply<T, VB, VPL>(out, old, acc, on, state, st_old, eta, (acc_t<T>)P.eps, nvec * V::NE, G, gl,
+                                          group_mask(G, threadIdx.x & 31));
+#pragma unroll
+                for (int p = 0; p < VPL; ++p)
+                    if (on[p]) st_plain<VB>(row + (size_t)(gl + p * G) * VB, &out[p]);
+            }
+        }
+        __syncthreads();  // the stages are reused by the next bucket
+    }
+}
+
 // ------------------------------------------------------------------------------------ host
 static int pick_vb_update(const etb_update_item& it) {
     const size_t es = elt_bytes(it.table.elt);
@@ -709,13 +845,21 @@ static UpdClass classify_update(const etb_update_item& it) {
     return c;
 }
 
-enum { kKernelMain = 0, kKernelTasks = 1, kKernelCombine = 2 };
+enum { kKernelMain = 0, kKernelTasks = 1, kKernelCombine = 2, kKernelStrictLong = 3 };
 
 template <typename T, int VB, int VPL, int OPT>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain) sgd_update_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
     else if (which == kKernelTasks) bucket_tasks_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
-    else long_combine_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
+    else if (which == kKernelStrictLong) {
+        constexpr int kSmem = kStrictStages * kStrictStageBytes;  // 96 KB of dynamic shared memory: opt in once
+        static thread_local bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(long_strict_kernel<T, VB, VPL, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            configured = true;
+        }
+        long_strict_kernel<T, VB, VPL, OPT><<<grid, kUThreads, kSmem, s>>>(P);
+    } else long_combine_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
 }
 
 template <typename T, int VB, int OPT>
@@ -845,6 +989,8 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         P.nslots = n;
         P.G = c.G;
         P.nvec = c.nvec;
+        // strict order: long buckets whose rows fit one pass (and one 32 KB stage) are streamed by long_strict_kernel
+        P.strict_long = (!P.split_long && c.nvec <= c.G * c.vpl && c.nvec * c.vb <= kStrictStageBytes) ? 1 : 0;
         ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
         const int64_t buckets_per_block = (kUThreads / 32) * 32 * ETB_UPDATE_RPL;  // one tile per warp
         const int grid = (int)((view->n_total + buckets_per_block - 1) / buckets_per_block);
@@ -855,6 +1001,12 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
             const int64_t max_tasks = view->n_total / (kShortMax + 1) + 1;
             const int gridT = (int)std::min<int64_t>((max_tasks + per_block - 1) / per_block, (int64_t)num_sms() * 8);
             launch_update(opt, kKernelTasks, c, gridT, stream, P);
+            ETB_LAUNCHED();
+        }
+        if (P.strict_long && view->n_total > kLongThreshold) {
+            const int64_t max_long = view->n_total / kLongThreshold + 1;
+            const int gridS = (int)std::min<int64_t>(max_long, (int64_t)num_sms() * 2);  // one CTA per long bucket
+            launch_update(opt, kKernelStrictLong, c, gridS, stream, P);
             ETB_LAUNCHED();
         }
         if (P.split_long && view->n_total > kLongThreshold) {

@@ -55,7 +55,7 @@ end
         Δ = randn(Float32, size(out)...)
         g = back(DeviceMatrix(Δ))[2]
         @test g isa SparseEmbeddingUpdate
-        update!((eta = 10.0,), table, g)
+        update!(Descent(10.0), table, g)
         dense = zeros(Float32, size(base))
         flat = vec(I)
         bag = reducing ? size(I, 1) : 1
@@ -64,4 +64,38 @@ end
         end
         @test isapprox(Array(parent(table)), base .- 10.0f0 .* dense)     # reference tolerance (isapprox)
     end
+end
+
+@testset "ensemble update, IndexerView, uncompress" begin     # reference test/update.jl:64-120, src/sparseupdate.jl:16-32
+    base = [randn(Float32, 64, 100) for _ in 1:4]
+    tables = [SimpleEmbedding{Static{64}}(DeviceMatrix(copy(b))) for b in base]
+    Is = [rand(1:100, 10, 50) for _ in 1:4]
+    out, back = ChainRulesCore.rrule(maplookup, PreallocationStrategy(8), tables, Is)
+    Δ = randn(Float32, size(out)...)
+    grads = back(DeviceMatrix(Δ))[3]
+    called = Ref(0)
+    update!(Descent(0.5), tables, grads, [Indexer()]; telemetry_cb = () -> (called[] += 1))
+    @test called[] == 1
+    for t in 1:4
+        dense = zeros(Float32, 64, 100)
+        for (p, c) in enumerate(vec(Is[t]))
+            dense[:, c] .+= Δ[8 + 64 * (t - 1) .+ (1:64), div(p - 1, 10) + 1]
+        end
+        @test isapprox(Array(parent(tables[t])), base[t] .- 0.5f0 .* dense)
+        @test isapprox(Array(uncompress(grads[t], 100)), dense)
+    end
+    # partitioned update == full update (reference test/update.jl:90-118)
+    a = SimpleEmbedding{Static{64}}(DeviceMatrix(copy(base[1])))
+    b = SimpleEmbedding{Static{64}}(DeviceMatrix(copy(base[1])))
+    g = SparseEmbeddingUpdate{Static{64}}(DeviceMatrix(Δ[9:72, :]), DeviceIndices(Is[1]))
+    ix = Indexer()
+    update!(Descent(0.5), a, g, ix)
+    index!(ix, b, g)
+    for j in 1:4
+        update!(b, g, IndexerView(ix, 4, j), 0.5)
+    end
+    @test Array(parent(a)) == Array(parent(b))
+    # undef constructor (reference src/split.jl:29-46)
+    s = SplitEmbedding{Static{16},Float32}(undef, 16, 1000, 300)
+    @test size(s) == (16, 1000)
 end

@@ -85,3 +85,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "README.md", f"{f} mentions the oracle"
+
+
+def build_abi_smoke(out_path):
+    """tests/abi_smoke.c -> a plain-C executable linked against libembtab_b200.so (no Python, no torch)"""
+    import subprocess
+    lib_dir = os.path.join(ROOT, "embeddingtables.jl_b200", "lib")
+    cmd = ["gcc", "-std=c99", "-O1", "-ffp-contract=off", "-Wall", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "abi_smoke.c"), "-L", lib_dir, "-lembtab_b200", f"-Wl,-rpath,{lib_dir}", "-lm",
+           "-o", out_path]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return out_path
+
+
+def test_abi_smoke_compiles_and_links_as_plain_c(tmp_path):
+    # the header is enough for a C compiler and every entry point the program uses resolves against the .so
+    exe = build_abi_smoke(str(tmp_path / "abi_smoke"))
+    assert os.path.exists(exe)

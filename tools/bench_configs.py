@@ -145,8 +145,12 @@ def config_c3(fh):
             t = timeit(lambda: E.update_(opt, table, grad, indexer), iters=10 if mode == "split" else 3,
                        warmup=2, flush=flush)
             ti = timeit(lambda: E.index_(indexer, table, grad), iters=10, warmup=2, flush=flush)
+            tg = timeit_graph(lambda: E.update_(opt, table, grad, indexer), iters=10, warmup=2, flush=flush)   # GPU time alone
+            tig = timeit_graph(lambda: E.index_(indexer, table, grad), iters=10, warmup=2, flush=flush)
             emit({"config": "C3", "form": name, "n": n, "distinct_rows": u, "hottest_row_members": top, "order": mode,
                   "update_us": t * 1e3, "index_us": ti * 1e3, "kernel_us": (t - ti) * 1e3,
+                  "update_us_graph": tg * 1e3, "index_us_graph": tig * 1e3, "gbs_graph": bytes_alg / tg / 1e6,
+                  "frac_of_measured_peak_graph": bytes_alg / tg / 1e6 / PEAK,
                   "lookups_per_sec": n / (t * 1e-3), "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / t / 1e6,
                   "frac_of_measured_peak": bytes_alg / t / 1e6 / PEAK}, fh)
         E.set_update_order("split")
