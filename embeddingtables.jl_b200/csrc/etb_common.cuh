@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -36,6 +37,14 @@ int32_t& launch_counter();  // thread-local: kernels launched by the current API
         ETB_CUDA(cudaGetLastError());                                                      \
     } while (0)
 
+// One NVTX range per API call (domain "embtab"): `nsys profile --trace=cuda,nvtx` shows every etb_* call with the
+// kernels it enqueued underneath.  Header-only NVTX v3: without a profiler attached a range is one untaken branch.
+struct ApiRange {
+    explicit ApiRange(const char* name) { nvtxRangePushA(name); }
+    ~ApiRange() { nvtxRangePop(); }
+};
+#define ETB_API_RANGE() ::etb::ApiRange etb_api_range_(__func__)
+
 inline size_t elt_bytes(int32_t elt) {
     return (elt == ETB_F16 || elt == ETB_BF16) ? 2 : ((elt == ETB_F32 || elt == ETB_I32) ? 4 : 8);
 }
@@ -55,11 +64,13 @@ inline int pow2ceil(int x) {
 // Compact device-side form of etb_table: the GPU `columnpointer`
 // (reference src/simple.jl:52-55, src/split.jl:59-65,81-86).
 struct DevTable {
-    const char* base;           // Simple
+    const char* base;           // Simple; Cached: the host-resident table
     const char* const* chunks;  // Split (device array)
     int64_t row_stride;         // bytes between embedding rows (ld * sizeof(T))
     uint32_t shard_rows;        // 0 = Simple
     uint32_t pad;
+    const char* cache_rows;     // Cached: the HBM row cache ...
+    const int32_t* slot_of_row; // ... and the slot of every row (-1 = on the host); null for Simple / Split
 };
 
 inline DevTable make_dev_table(const etb_table& t) {
@@ -69,6 +80,15 @@ inline DevTable make_dev_table(const etb_table& t) {
     d.row_stride = (int64_t)t.ld * (int64_t)elt_bytes(t.elt);
     d.shard_rows = t.chunks ? (uint32_t)t.shard_rows : 0u;
     d.pad = 0;
+    d.cache_rows = nullptr;
+    d.slot_of_row = nullptr;
+    if (t.chunks && t.shard_rows == ETB_TABLE_CACHED) {  // `chunks` is a host pointer to the cache descriptor
+        const etb_cache_desc* c = (const etb_cache_desc*)t.chunks;
+        d.chunks = nullptr;
+        d.shard_rows = 0xffffffffu;
+        d.cache_rows = (const char*)c->rows;
+        d.slot_of_row = c->slot_of_row;
+    }
     return d;
 }
 
@@ -79,6 +99,10 @@ int32_t validate_table(const etb_table& t, const char* who);
 __device__ __forceinline__ const char* row_ptr(const DevTable& t, int64_t i1) {
     uint64_t z = (uint64_t)(i1 - 1);
     if (t.shard_rows == 0) return t.base + z * (uint64_t)t.row_stride;
+    if (t.slot_of_row) {  // host-tier table: the row's HBM copy when it has one
+        const int32_t s = __ldg(t.slot_of_row + z);
+        return s >= 0 ? t.cache_rows + (uint64_t)s * (uint64_t)t.row_stride : t.base + z * (uint64_t)t.row_stride;
+    }
     uint64_t chunk, within;
     if (z <= 0xffffffffull) {  // 32-bit divide is ~4x cheaper than the 64-bit one
         uint32_t z32 = (uint32_t)z;

@@ -292,6 +292,7 @@ int32_t etb_index_workspace_bytes(const etb_update_item* items_host, int32_t n_i
 
 int32_t etb_index(void* workspace, size_t workspace_bytes, const etb_update_item* items_host, int32_t n_items,
                   etb_index_view* view_host, void* stream) {
+    ETB_API_RANGE();
     launch_counter() = 0;
     return index_impl(workspace, workspace_bytes, items_host, n_items, view_host, (cudaStream_t)stream);
 }

@@ -30,10 +30,10 @@
 namespace etb {
 
 constexpr int kThreads = 256;
-constexpr int kMaxItems = 256;   // descriptors per launch (kernel-parameter space: 256*72 B = 18 KB of 32 KB)
+constexpr int kMaxItems = 256;   // descriptors per launch (kernel-parameter space: 256*88 B = 22 KB of 32 KB)
 constexpr int kGatherCols = 4;   // columns per group in the gather kernel (loads in flight)
 
-struct LookupDesc {  // 72 bytes
+struct LookupDesc {  // 88 bytes
     DevTable table;
     const void* idx;
     char* dst;
@@ -433,11 +433,13 @@ using namespace etb;
 extern "C" {
 
 int32_t etb_maplookup(const etb_lookup_item* items_host, int32_t n_items, void* stream) {
+    ETB_API_RANGE();
     return maplookup_impl(items_host, n_items, (cudaStream_t)stream);
 }
 
 int32_t etb_gather(void* dst, int64_t ld_dst, const etb_table* table_host, const void* idx,
                    int32_t idx_elt, int64_t n, void* stream) {
+    ETB_API_RANGE();
     ETB_REQUIRE(table_host, "etb_gather: null table");
     etb_lookup_item it;
     memset(&it, 0, sizeof(it));
@@ -454,6 +456,7 @@ int32_t etb_gather(void* dst, int64_t ld_dst, const etb_table* table_host, const
 
 int32_t etb_pooled_sum(void* dst, int64_t ld_dst, const etb_table* table_host, const void* idx,
                        int32_t idx_elt, int64_t bag, int64_t batch, int64_t ld_idx, void* stream) {
+    ETB_API_RANGE();
     ETB_REQUIRE(table_host, "etb_pooled_sum: null table");
     ETB_REQUIRE(bag >= 1, "etb_pooled_sum: bag must be >= 1 (got %lld)", (long long)bag);
     etb_lookup_item it;

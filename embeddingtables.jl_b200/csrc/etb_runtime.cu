@@ -41,7 +41,12 @@ int32_t validate_table(const etb_table& t, const char* who) {
     ETB_REQUIRE(t.dim > 0, "%s: table dim must be positive (got %d)", who, t.dim);
     ETB_REQUIRE(t.ld >= t.dim, "%s: table ld (%d) < dim (%d)", who, t.ld, t.dim);
     ETB_REQUIRE(t.nrows >= 0, "%s: negative nrows", who);
-    if (t.chunks) {
+    if (t.chunks && t.shard_rows == ETB_TABLE_CACHED) {
+        const etb_cache_desc* c = (const etb_cache_desc*)t.chunks;
+        ETB_REQUIRE(t.base && c->rows && c->slot_of_row && c->row_of_slot && c->cursor && c->capacity >= 0,
+                    "%s: cached table needs base, rows, slot_of_row, row_of_slot and cursor", who);
+        ETB_REQUIRE(t.nrows <= 0x7fffffffll && c->capacity <= 0x7fffffffll, "%s: cached table: more than 2^31 rows / slots", who);
+    } else if (t.chunks) {
         ETB_REQUIRE(t.shard_rows > 0 && t.shard_rows <= 0xffffffffll,
                     "%s: split table needs 0 < shard_rows < 2^32 (got %lld)", who, (long long)t.shard_rows);
     } else {
@@ -108,6 +113,7 @@ int32_t etb_free_host(void* ptr_host) {
 }
 
 int32_t etb_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stream) {
+    ETB_API_RANGE();
     if (bytes == 0) return ETB_OK;
     ETB_REQUIRE(dst && src_host, "etb_memcpy_h2d: null pointer");
     ETB_CUDA(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
@@ -115,6 +121,7 @@ int32_t etb_memcpy_h2d(void* dst, const void* src_host, size_t bytes, void* stre
 }
 
 int32_t etb_memcpy_d2h(void* dst_host, const void* src, size_t bytes, void* stream) {
+    ETB_API_RANGE();
     if (bytes == 0) return ETB_OK;
     ETB_REQUIRE(dst_host && src, "etb_memcpy_d2h: null pointer");
     ETB_CUDA(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -130,6 +137,7 @@ int32_t etb_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
 
 int32_t etb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size_t src_pitch, size_t width_bytes,
                          size_t height, void* stream) {
+    ETB_API_RANGE();
     if (width_bytes == 0 || height == 0) return ETB_OK;
     ETB_REQUIRE(dst && src_host, "etb_memcpy2d_h2d: null pointer");
     ETB_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "etb_memcpy2d_h2d: pitch smaller than the run");
@@ -140,6 +148,7 @@ int32_t etb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size
 
 int32_t etb_memcpy2d_d2h(void* dst_host, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
                          size_t height, void* stream) {
+    ETB_API_RANGE();
     if (width_bytes == 0 || height == 0) return ETB_OK;
     ETB_REQUIRE(dst_host && src, "etb_memcpy2d_d2h: null pointer");
     ETB_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "etb_memcpy2d_d2h: pitch smaller than the run");

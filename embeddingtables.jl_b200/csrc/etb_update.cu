@@ -25,6 +25,7 @@
 // bucket, added in a fixed order).  The only atomics are worklist cursors; nothing that reaches a
 // result depends on their order.
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "etb_common.cuh"
@@ -46,7 +47,7 @@ constexpr int kUThreads = 256;
 constexpr int kUMaxItems = 96;
 
 // ------------------------------------------------------------------------------------ K5
-struct UpdDesc {  // 48 bytes
+struct UpdDesc {  // 64 bytes
     DevTable table;
     const char* delta;
     int64_t ld_delta_bytes;
@@ -683,7 +684,7 @@ long_combine_kernel(const __grid_constant__ UpdParams P) {
 // the member rows into shared memory with cp.async (4 stages of up to 64 rows), and the first G lanes add them from
 // there in order (C3's hottest row has 45 k members: measurements in profiles/README.md).
 constexpr int kStrictStageBytes = 24 * 1024, kStrictStages = 4, kStrictMaxRows = 48;  // 96 KB: two CTAs per SM
-constexpr int kStrictPieces = 6;  // VB-byte pieces per thread and batch (a batch has at most 6 * 256 of them)
+constexpr int kStrictPieces = 7;  // VB-byte pieces per producer thread and batch (a batch has at most 7 * 224 of them)
 
 template <int VB>
 __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
@@ -701,16 +702,18 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
     extern __shared__ __align__(16) char s_rows[];  // [kStrictStages][rows_per_stage][nvec * VB]
     const int G = P.G, nvec = P.nvec;
     const int row_bytes = nvec * VB;
-    const int rows_per_stage = min(min(kStrictMaxRows, kStrictStageBytes / row_bytes), kStrictPieces * kUThreads / nvec);
+    const int rows_per_stage = min(min(kStrictMaxRows, kStrictStageBytes / row_bytes), kStrictPieces * (kUThreads - 32) / nvec);
     const int gl = threadIdx.x & (G - 1);
-    const bool consumer = threadIdx.x < G;  // group 0 = the first G lanes of warp 0
-    // my pieces of a batch: piece pc = tid + k * 256 is vector pv[k] of the batch's row pr[k] -- the same for every
-    // batch, so the divisions happen once per kernel
+    const bool consumer = threadIdx.x < G;  // group 0 = the first G lanes of warp 0 add; warp 0 never loads,
+    const bool producer = threadIdx.x >= 32;  // warps 1..7 never add
+    constexpr int kProducers = kUThreads - 32;
+    // a producer's pieces of a batch: piece pc = (tid - 32) + k * 224 is vector pv[k] of the batch's row pr[k] -- the
+    // same for every batch, so the divisions happen once per kernel
     int pr[kStrictPieces], pv[kStrictPieces];
 #pragma unroll
     for (int k = 0; k < kStrictPieces; ++k) {
-        const int pc = threadIdx.x + k * kUThreads;
-        pr[k] = pc / nvec;
+        const int pc = (int)threadIdx.x - 32 + k * kProducers;
+        pr[k] = producer ? pc / nvec : rows_per_stage;  // warp 0: no pieces
         pv[k] = pc - pr[k] * nvec;
     }
     const uint32_t n_long = P.counters->n_long;
@@ -726,16 +729,19 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
         const UpdDesc& d = P.item[slot];
         char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
         const int nbatch = (int)((stop - start + rows_per_stage - 1) / rows_per_stage);
-        // all threads: member rows of batch b -> stage b % 3, one VB-byte piece per thread and step
+        // producers: delta columns of my pieces' members in batch b (independent loads; issued one batch ahead of use)
+        int32_t col[kStrictPieces];
+        auto load_map = [&](int b) {
+            const int64_t m0 = start + (int64_t)b * rows_per_stage;
+            const int rows = b < nbatch ? (int)min((int64_t)rows_per_stage, stop - m0) : 0;
+#pragma unroll
+            for (int k = 0; k < kStrictPieces; ++k) col[k] = pr[k] < rows ? __ldg(P.map + m0 + pr[k]) : 0;
+        };
+        // producers: member rows of batch b -> stage b % kStrictStages, one VB-byte piece per thread and step
         auto issue = [&](int b) {
             if (b < nbatch) {
-                const int64_t m0 = start + (int64_t)b * rows_per_stage;
-                const int rows = (int)min((int64_t)rows_per_stage, stop - m0);
+                const int rows = (int)min((int64_t)rows_per_stage, stop - (start + (int64_t)b * rows_per_stage));
                 char* stage = s_rows + (size_t)(b % kStrictStages) * rows_per_stage * row_bytes;
-                int32_t col[kStrictPieces];
-#pragma unroll
-                for (int k = 0; k < kStrictPieces; ++k)  // the delta columns of my pieces' members first (independent loads)
-                    col[k] = pr[k] < rows ? __ldg(P.map + m0 + pr[k]) : 0;
 #pragma unroll
                 for (int k = 0; k < kStrictPieces; ++k)
                     if (pr[k] < rows)
@@ -759,21 +765,42 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
             state = (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask);
             st_old = *state;
         }
-        issue(0);
-        issue(1);
-        issue(2);
+        for (int b = 0; b < kStrictStages - 1; ++b) {
+            load_map(b);
+            issue(b);
+        }
+        load_map(kStrictStages - 1);
         for (int b = 0; b < nbatch; ++b) {
-            asm volatile("cp.async.wait_group 2;" ::: "memory");  // my pieces of batch b have landed
-            __syncthreads();                                      // everybody's have; stage (b + 3) % 4 is free again
-            issue(b + 3);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kStrictStages - 2) : "memory");  // my pieces of batch b have landed
+            __syncthreads();  // everybody's have; the stage of batch b - 1 is free again
+            issue(b + kStrictStages - 1);     // with the columns loaded one iteration ago
+            load_map(b + kStrictStages);      // in flight until the next iteration
             if (consumer) {
                 const int rows = (int)min((int64_t)rows_per_stage, stop - (start + (int64_t)b * rows_per_stage));
                 const char* stage = s_rows + (size_t)(b % kStrictStages) * rows_per_stage * row_bytes;
-                for (int r = 0; r < rows; ++r) {
+                // U rows from shared memory into registers, then their additions in order: the shared-memory latency is
+                // paid once per U rows instead of once per row
+                constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+                const char* mine_s = stage + (size_t)gl * VB;
+                int r = 0;
+                for (; r + U <= rows; r += U) {
+                    V v[U][VPL];
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p)
+                            if (on[p]) v[u][p] = *(const V*)(mine_s + (size_t)(r + u) * row_bytes + (size_t)p * G * VB);
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p)
+                            if (on[p]) acc_add(acc[p], v[u][p]);
+                }
+                for (; r < rows; ++r) {
 #pragma unroll
                     for (int p = 0; p < VPL; ++p) {
                         if (on[p]) {
-                            const V v = *(const V*)(stage + (size_t)r * row_bytes + (size_t)(gl + p * G) * VB);
+                            const V v = *(const V*)(mine_s + (size_t)r * row_bytes + (size_t)p * G * VB);
                             acc_add(acc[p], v);
                         }
                     }
@@ -1104,6 +1131,93 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, voi
     return ETB_OK;
 }
 
+// ------------------------------------------------------------------------------------ host-tier tables
+// Admission (Update phase): one warp per bucket.  A bucket of a cached table whose row still lives on the host and
+// that had >= min_count members takes the next free slot; the warp copies the row into it and only then publishes
+// the slot (no other kernel touches the table meanwhile: stream order).
+struct CacheItem {
+    const char* host_rows;
+    char* cache_rows;
+    int32_t* slot_of_row;
+    int32_t* row_of_slot;
+    int32_t* cursor;
+    int64_t row_stride, row_bytes;
+    int32_t capacity, pad;
+};
+struct CacheParams {
+    CacheItem item[kUMaxItems];
+    const BucketRec* recs;
+    const int64_t* nnz;
+    int64_t n_total;
+    int32_t row_bits, min_count, n_items;
+};
+
+__global__ void __launch_bounds__(256) cache_admit_kernel(const __grid_constant__ CacheParams P) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nnz = *P.nnz;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < nnz; b += (int64_t)gridDim.x * 8) {
+        const BucketRec rec = P.recs[b];
+        const int slot_id = (int)(rec.key >> P.row_bits);
+        if (slot_id >= P.n_items) continue;
+        const CacheItem& c = P.item[slot_id];
+        if (!c.slot_of_row) continue;  // not a host-tier table
+        const int64_t stop = (b + 1 < nnz) ? (int64_t)P.recs[b + 1].start : P.n_total;
+        const int64_t row = (int64_t)(rec.key & row_mask);
+        int s = -1;
+        if (lane == 0 && stop - (int64_t)rec.start >= P.min_count && c.slot_of_row[row] < 0) {
+            s = atomicAdd(c.cursor, 1);
+            if (s >= c.capacity) {  // full: undo (the cursor never runs away)
+                atomicSub(c.cursor, 1);
+                s = -1;
+            }
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s < 0) continue;
+        const char* src = c.host_rows + row * c.row_stride;
+        char* dst = c.cache_rows + (int64_t)s * c.row_stride;
+        if (((c.row_bytes | c.row_stride | (int64_t)(uintptr_t)c.host_rows | (int64_t)(uintptr_t)c.cache_rows) & 15) == 0)
+            for (int64_t o = lane * 16; o < c.row_bytes; o += 32 * 16) *(uint4*)(dst + o) = *(const uint4*)(src + o);
+        else
+            for (int64_t o = lane; o < c.row_bytes; o += 32) dst[o] = src[o];
+        __syncwarp();
+        if (lane == 0) {
+            c.row_of_slot[s] = (int32_t)row;
+            __threadfence();
+            c.slot_of_row[row] = s;
+        }
+    }
+}
+
+// write every cached row back to the host table: one warp per slot
+__global__ void __launch_bounds__(256) cache_flush_kernel(CacheItem c) {
+    const int lane = threadIdx.x & 31;
+    const int used = min(*c.cursor, c.capacity);
+    for (int s = blockIdx.x * 8 + (threadIdx.x >> 5); s < used; s += gridDim.x * 8) {
+        const char* src = c.cache_rows + (int64_t)s * c.row_stride;
+        char* dst = const_cast<char*>(c.host_rows) + (int64_t)c.row_of_slot[s] * c.row_stride;
+        if (((c.row_bytes | c.row_stride | (int64_t)(uintptr_t)c.host_rows | (int64_t)(uintptr_t)c.cache_rows) & 15) == 0)
+            for (int64_t o = lane * 16; o < c.row_bytes; o += 32 * 16) *(uint4*)(dst + o) = *(const uint4*)(src + o);
+        else
+            for (int64_t o = lane; o < c.row_bytes; o += 32) dst[o] = src[o];
+    }
+}
+
+static bool make_cache_item(const etb_table& t, CacheItem& c) {
+    memset(&c, 0, sizeof(c));
+    if (!(t.chunks && t.shard_rows == ETB_TABLE_CACHED)) return false;
+    const etb_cache_desc* d = (const etb_cache_desc*)t.chunks;
+    c.host_rows = (const char*)t.base;
+    c.cache_rows = (char*)d->rows;
+    c.slot_of_row = d->slot_of_row;
+    c.row_of_slot = d->row_of_slot;
+    c.cursor = d->cursor;
+    c.row_stride = (int64_t)t.ld * (int64_t)elt_bytes(t.elt);
+    c.row_bytes = (int64_t)t.dim * (int64_t)elt_bytes(t.elt);
+    c.capacity = (int32_t)d->capacity;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------ peer-memory barrier
 // One warp: lane r tells rank r "rank `me` has reached `epoch`" with a release store into r's flag array (peer
 // memory over NVLink), then waits until rank r has told me the same.  The kernels before this one on the stream
@@ -1129,12 +1243,14 @@ extern "C" {
 
 int32_t etb_sgd_update(const etb_index_view* view_host, const etb_update_item* items_host, int32_t n_items, double eta,
                        int32_t flags, void* stream) {
+    ETB_API_RANGE();
     launch_counter() = 0;
     return update_impl(view_host, items_host, n_items, eta, flags, (cudaStream_t)stream);
 }
 
 int32_t etb_adagrad_update(const etb_index_view* view_host, const etb_update_item* items_host, void* const* states_host,
                            int32_t n_items, double eta, double eps, int32_t flags, void* stream) {
+    ETB_API_RANGE();
     launch_counter() = 0;
     ETB_REQUIRE(eps >= 0.0, "etb_adagrad_update: negative eps");
     return update_impl(view_host, items_host, n_items, eta, flags & ~ETB_UPDATE_FMA, (cudaStream_t)stream, kOptAdagrad,
@@ -1143,6 +1259,7 @@ int32_t etb_adagrad_update(const etb_index_view* view_host, const etb_update_ite
 
 int32_t etb_index_and_update(void* workspace, size_t workspace_bytes, const etb_update_item* items_host,
                              int32_t n_items, double eta, int32_t flags, void* stream) {
+    ETB_API_RANGE();
     launch_counter() = 0;
     etb_index_view view;
     if (int32_t st = index_impl(workspace, workspace_bytes, items_host, n_items, &view, (cudaStream_t)stream)) return st;
@@ -1151,6 +1268,7 @@ int32_t etb_index_and_update(void* workspace, size_t workspace_bytes, const etb_
 
 int32_t etb_uncompress(void* dst, int64_t ld_dst, int32_t dim, int32_t elt, const void* delta, int64_t ld_delta,
                        const void* idx, int32_t idx_elt, int64_t bag, int64_t batch, int64_t ld_idx, void* stream) {
+    ETB_API_RANGE();
     launch_counter() = 0;
     ETB_REQUIRE(elt == ETB_F32 || elt == ETB_F64, "etb_uncompress: only Float32/Float64");
     ETB_REQUIRE(idx_elt_valid(idx_elt), "etb_uncompress: bad index type");
@@ -1172,31 +1290,80 @@ int32_t etb_uncompress(void* dst, int64_t ld_dst, int32_t dim, int32_t elt, cons
 
 int32_t etb_a2a_unpack(void* dst, int64_t ld_dst, const void* recv, const int64_t* rows_host, const int64_t* row_off_host,
                        int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
+    ETB_API_RANGE();
     return a2a_copy(true, dst, ld_dst, const_cast<void*>(recv), nullptr, rows_host, row_off_host, nranks, batch_local,
                     elt, (cudaStream_t)stream);
 }
 
 int32_t etb_a2a_pack(void* send, const void* src, int64_t ld_src, const int64_t* rows_host, const int64_t* row_off_host,
                      int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
+    ETB_API_RANGE();
     return a2a_copy(false, const_cast<void*>(src), ld_src, send, nullptr, rows_host, row_off_host, nranks, batch_local,
                     elt, (cudaStream_t)stream);
 }
 
 int32_t etb_a2a_scatter(void* const* dst_ptrs_host, const void* src, int64_t ld_src, const int64_t* rows_host,
                         const int64_t* row_off_host, int32_t nranks, int64_t batch_local, int32_t elt, void* stream) {
+    ETB_API_RANGE();
     return a2a_copy(false, const_cast<void*>(src), ld_src, nullptr, dst_ptrs_host, rows_host, row_off_host, nranks,
                     batch_local, elt, (cudaStream_t)stream);
+}
+
+int32_t etb_cache_admit(const etb_index_view* view_host, const etb_update_item* items_host, int32_t n_items,
+                        int32_t min_count, void* stream) {
+    ETB_API_RANGE();
+    launch_counter() = 0;
+    ETB_REQUIRE(view_host && (n_items == 0 || items_host) && n_items >= 0, "etb_cache_admit: bad arguments");
+    if (view_host->n_total == 0) return ETB_OK;
+    static thread_local CacheParams P;
+    for (int i0 = 0; i0 < n_items; i0 += kUMaxItems) {  // bucket keys carry the table slot: one launch per 96 tables
+        const int n = std::min(kUMaxItems, n_items - i0);
+        bool any = false;
+        // the kernel decodes slot = key >> row_bits over the whole call; give it this group's tables at their slots
+        for (int j = 0; j < n; ++j) {
+            if (int32_t st = validate_table(items_host[i0 + j].table, "etb_cache_admit")) return st;
+            any = make_cache_item(items_host[i0 + j].table, P.item[j]) || any;
+        }
+        if (!any) continue;
+        ETB_REQUIRE(i0 == 0, "etb_cache_admit: host-tier tables must be among the first %d tables of an ensemble", kUMaxItems);
+        P.recs = (const BucketRec*)view_host->records;
+        P.nnz = view_host->nnz;
+        P.n_total = view_host->n_total;
+        P.row_bits = view_host->row_bits;
+        P.min_count = std::max(1, min_count);
+        P.n_items = n;
+        const int grid = (int)std::min<int64_t>((view_host->n_total + 7) / 8, (int64_t)num_sms() * 8);
+        cache_admit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        ETB_LAUNCHED();
+    }
+    return ETB_OK;
+}
+
+int32_t etb_cache_flush(const etb_table* table_host, void* stream) {
+    ETB_API_RANGE();
+    launch_counter() = 0;
+    ETB_REQUIRE(table_host, "etb_cache_flush: null table");
+    if (int32_t st = validate_table(*table_host, "etb_cache_flush")) return st;
+    CacheItem c;
+    ETB_REQUIRE(make_cache_item(*table_host, c), "etb_cache_flush: not an ETB_TABLE_CACHED table");
+    if (c.capacity == 0) return ETB_OK;
+    const int grid = std::min((c.capacity + 7) / 8, num_sms() * 8);
+    cache_flush_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c);
+    ETB_LAUNCHED();
+    return ETB_OK;
 }
 
 int32_t etb_a2a_scatter_ld(void* const* dst_ptrs_host, const int64_t* dst_ld_host, const void* src, int64_t ld_src,
                            const int64_t* rows_host, const int64_t* row_off_host, int32_t nranks, int64_t batch_local,
                            int32_t elt, void* stream) {
+    ETB_API_RANGE();
     ETB_REQUIRE(dst_ld_host, "etb_a2a_scatter_ld: null leading dimensions");
     return a2a_copy(false, const_cast<void*>(src), ld_src, nullptr, dst_ptrs_host, rows_host, row_off_host, nranks,
                     batch_local, elt, (cudaStream_t)stream, dst_ld_host);
 }
 
 int32_t etb_peer_barrier(void* const* flag_ptrs_host, int32_t rank, int32_t nranks, uint32_t epoch, void* stream) {
+    ETB_API_RANGE();
     launch_counter() = 0;
     ETB_REQUIRE(nranks >= 1 && nranks <= 16 && rank >= 0 && rank < nranks, "etb_peer_barrier: bad rank %d of %d", rank, nranks);
     ETB_REQUIRE(flag_ptrs_host, "etb_peer_barrier: null flag pointers");

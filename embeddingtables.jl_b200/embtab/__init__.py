@@ -5,6 +5,7 @@ Julia's `f!` is spelled `f_`.  Device memory comes from PyTorch; every computati
 into the sm_100a C-ABI library.  There is no CPU fallback.
 """
 from ._lib import EmbTabError, LIB_PATH, lib
+from .cached import CachedEmbedding
 from .darray import DeviceArray, as_device, as_device_indices, bfloat16, pinned_empty
 from .graph import capture
 from .lookup import (AbstractExecutionStrategy, ColumnWrap, DefaultStrategy, PreallocationStrategy,

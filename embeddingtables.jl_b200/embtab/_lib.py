@@ -90,6 +90,8 @@ _SIGS = {
     "etb_a2a_scatter_ld": ([C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p, C.c_int64, C.POINTER(C.c_int64),
                             C.POINTER(C.c_int64), C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
     "etb_peer_barrier": ([C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_uint32, C.c_void_p], C.c_int32),
+    "etb_cache_admit": ([C.POINTER(IndexView), C.POINTER(UpdateItem), C.c_int32, C.c_int32, C.c_void_p], C.c_int32),
+    "etb_cache_flush": ([C.POINTER(Table), C.c_void_p], C.c_int32),
     "etb_a2a_pack": ([C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                       C.c_int32, C.c_int64, C.c_int32, C.c_void_p], C.c_int32),
 }

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from .darray import DeviceArray, as_device_indices, current_stream_ptr
-from .tables import AbstractEmbeddingTable, example, featuresize
+from .tables import AbstractEmbeddingTable, Forward, device_descriptor, example, featuresize
 
 
 # ------------------------------------------------------------------------------ destinations
@@ -39,7 +39,7 @@ def _item(table, I: DeviceArray, dst: DeviceArray) -> _lib.LookupItem:
         raise ValueError(f"destination {dst.shape} too small for {featuresize(table)} x {batch}")
     if dst.dtype != table.dtype:
         raise TypeError(f"destination eltype {dst.dtype} != table eltype {table.dtype}")
-    return _lib.LookupItem(table.descriptor(), I.ptr, dst.ptr, dst.ld, batch, bag, ld_idx, I.elt, 0)
+    return _lib.LookupItem(device_descriptor(table, Forward()), I.ptr, dst.ptr, dst.ld, batch, bag, ld_idx, I.elt, 0)
 
 
 def _run(items):

@@ -16,7 +16,7 @@ from . import _lib
 from .darray import DeviceArray, as_device, as_device_indices, current_stream_ptr
 from .lookup import (AbstractExecutionStrategy, DefaultStrategy, PreallocationStrategy, colwrap, lookup,
                      maplookup)
-from .tables import AbstractEmbeddingTable, Static, featuresize
+from .tables import AbstractEmbeddingTable, Static, Update, device_descriptor, featuresize
 
 
 class Descent:
@@ -66,7 +66,7 @@ def _update_item(table, grad: SparseEmbeddingUpdate) -> _lib.UpdateItem:
         raise TypeError(f"delta eltype {d.dtype} != table eltype {table.dtype}")
     if d.shape[0] < featuresize(table) or d.shape[1] < batch:
         raise ValueError(f"delta {d.shape} too small for {featuresize(table)} x {batch}")
-    return _lib.UpdateItem(table.descriptor(), d.ptr, d.ld, I.ptr, batch, bag, ld_idx, I.elt,
+    return _lib.UpdateItem(device_descriptor(table, Update()), d.ptr, d.ld, I.ptr, batch, bag, ld_idx, I.elt,
                            _flags(table) & _lib.UPDATE_FMA)   # the epilogue is a per-table choice
 
 
@@ -160,7 +160,7 @@ def _index_item(table, g) -> _lib.UpdateItem:
     if isinstance(g, _IndicesOnly):
         I = g.indices
         bag, batch, ld_idx = (0, I.shape[0], 0) if I.ndim == 1 else (I.shape[0], I.shape[1], I.ld)
-        return _lib.UpdateItem(table.descriptor(), None, featuresize(table), I.ptr, batch, bag, ld_idx, I.elt, 0)
+        return _lib.UpdateItem(device_descriptor(table, Update()), None, featuresize(table), I.ptr, batch, bag, ld_idx, I.elt, 0)
     return _update_item(table, g)
 
 
@@ -251,8 +251,13 @@ def _apply(tables, grads, indexer, eta, opt=None):
         states = (C.c_void_p * len(items))(*[opt.state(t).ptr for t in tables])
         _lib.check(_lib.lib().etb_adagrad_update(C.byref(view), base._items, states, len(items), opt.eta, opt.eps,
                                                  flags, stream))
-        return
-    _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(items), float(eta), flags, stream))
+    else:
+        _lib.check(_lib.lib().etb_sgd_update(C.byref(view), base._items, len(items), float(eta), flags, stream))
+    # Update-phase hook of table types that react to the access phase (host-tier tables admit the batch's hot rows
+    # into their HBM cache from the bucket records index! just produced)
+    hooks = [t for t in tables if hasattr(t, "after_update")]
+    if hooks:
+        hooks[0].after_update(base, base._items, len(items))
 
 
 def update_table_(table, update: SparseEmbeddingUpdate, indexer, alpha, nontemporal=True, *args):

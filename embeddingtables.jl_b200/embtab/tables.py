@@ -68,6 +68,16 @@ class Update(IndexingContext):
     pass
 
 
+def device_descriptor(table, ctx: IndexingContext):
+    """table.descriptor(ctx), tolerating table types whose descriptor() takes no context"""
+    fn = table.descriptor
+    try:
+        takes_ctx = fn.__func__.__code__.co_argcount >= 2
+    except AttributeError:
+        takes_ctx = True
+    return fn(ctx) if takes_ctx else fn()
+
+
 class AbstractEmbeddingTable:
     """AbstractEmbeddingTable{S,T}.  A subtype provides: `lookup_type` (S), `dtype` (T), `size()`,
     `columnpointer(i)`, `example()` and `descriptor()` -- the device form of `columnpointer` that
@@ -86,7 +96,9 @@ class AbstractEmbeddingTable:
     def example(self) -> DeviceArray:
         raise NotImplementedError
 
-    def descriptor(self) -> _lib.Table:
+    def descriptor(self, ctx: IndexingContext = None) -> _lib.Table:
+        """device form of columnpointer(table, i, ctx): `ctx` is Forward() from the lookups and Update() from update!
+        (reference src/lookup.jl:57-161, src/sparseupdate.jl:25-122); most tables ignore it"""
         raise NotImplementedError
 
     # --- AbstractArray interface (reference src/EmbeddingTables.jl:144-156): scalar access via
@@ -190,7 +202,7 @@ class SimpleEmbedding(AbstractEmbeddingTable):
     def example(self):
         return self.data
 
-    def descriptor(self):
+    def descriptor(self, ctx=None):
         d = self.data
         ld = self.lookup_type.N if isinstance(self.lookup_type, Static) else d.ld
         return _lib.Table(d.ptr, None, d.shape[1], 0, d.shape[0], ld, d.elt, 0)
@@ -263,7 +275,7 @@ class SplitEmbedding(AbstractEmbeddingTable):
     def example(self):
         return self.data[0]
 
-    def descriptor(self):
+    def descriptor(self, ctx=None):
         fs, shard = self.matrixsize
         return _lib.Table(None, self._chunk_ptrs.data_ptr(), self.size()[1], shard, fs, fs,
                           self.data[0].elt, 0)

@@ -89,15 +89,36 @@ enum {
  *       chunks[(i-1) / shard_rows] + ((i-1) % shard_rows)*ld*sizeof(T)
  */
 typedef struct etb_table {
-    void* base;          /* Simple: address of embedding row 1.  Split: NULL            */
-    void* const* chunks; /* Split: DEVICE array of chunk base pointers.  Simple: NULL   */
+    void* base;          /* Simple: address of embedding row 1.  Split: NULL.  Cached: row 1 of the HOST-resident
+                          * table (page-locked, device-addressable)                      */
+    void* const* chunks; /* Split: DEVICE array of chunk base pointers.  Simple: NULL.  Cached: HOST pointer to
+                          * an etb_cache_desc                                            */
     int64_t nrows;       /* embedding rows (Julia size(table, 2))                       */
-    int64_t shard_rows;  /* Split: rows per chunk (cols_per_shard).  Simple: 0          */
+    int64_t shard_rows;  /* Split: rows per chunk (cols_per_shard).  Simple: 0.  Cached: ETB_TABLE_CACHED */
     int32_t dim;         /* featuresize (Julia size(table, 1)), elements                */
     int32_t ld;          /* elements between consecutive embedding rows (>= dim)        */
     int32_t elt;         /* etb_dtype                                                   */
     int32_t reserved;
 } etb_table;
+
+/*
+ * Host-tier table with an HBM row cache (no reference counterpart -- the hook the reference leaves for
+ * it is the IndexingContext argument of columnpointer, src/EmbeddingTables.jl:74-77, 87-93, which lets a table
+ * resolve a row differently in the Forward and Update phases).  The whole table lives in page-locked host memory
+ * that the GPU can address (`base`); `rows` caches up to `capacity` of its rows in HBM and `slot_of_row` says which.
+ * Every kernel resolves a row as  slot_of_row[i-1] >= 0 ? rows + slot*ld : base + (i-1)*ld,  so results are bit for
+ * bit those of an all-HBM table.  A cached row is authoritative in HBM (update! writes it there) until
+ * etb_cache_flush copies it back.  etb_cache_admit, run after update! (the Update phase), admits the rows that the
+ * batch touched at least `min_count` times while slots are free.
+ */
+#define ETB_TABLE_CACHED (-1)
+typedef struct etb_cache_desc { /* a HOST struct of DEVICE pointers */
+    void* rows;            /* capacity x ld elements                                       */
+    int32_t* slot_of_row;  /* nrows entries: cache slot of each row, -1 = lives on the host */
+    int32_t* row_of_slot;  /* capacity entries: 0-based row held by each slot in use        */
+    int32_t* cursor;       /* one int32: slots in use                                       */
+    int64_t capacity;
+} etb_cache_desc;
 
 /*
  * One table's share of an ensemble lookup: replaces one `lookup!(out[i], x[i], I[i])`
@@ -261,6 +282,15 @@ int32_t etb_adagrad_update(const etb_index_view* view_host, const etb_update_ite
 int32_t etb_index_and_update(void* workspace, size_t workspace_bytes,
                              const etb_update_item* items_host, int32_t n_items, double eta,
                              int32_t flags, void* stream);
+
+/* Host-tier tables (etb_cache_desc above).  etb_cache_admit: for every bucket of `view` (the result of etb_index on
+ * these items) whose table is ETB_TABLE_CACHED, whose row is not cached yet and which has >= min_count members, take
+ * a free slot, copy the row from host memory into it and publish it in slot_of_row.  Call it when no kernel that
+ * uses the tables is in flight on another stream (it is stream-ordered on `stream`).  etb_cache_flush: copy every
+ * cached row back to the host table (the cache stays valid). */
+int32_t etb_cache_admit(const etb_index_view* view_host, const etb_update_item* items_host, int32_t n_items,
+                        int32_t min_count, void* stream);
+int32_t etb_cache_flush(const etb_table* table_host, void* stream);
 
 /* Debug/test helper: dense gradient of a SparseEmbeddingUpdate.
  * dst (dim x ncols, ld_dst) must be zeroed by the caller; accumulates in occurrence order.

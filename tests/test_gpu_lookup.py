@@ -122,7 +122,7 @@ def test_split_lookup(E, O, rows, shard):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int32, np.int64])
-@pytest.mark.parametrize("dim", [1, 3, 5, 6, 16, 20, 33, 80, 100, 130])
+@pytest.mark.parametrize("dim", [1, 3, 5, 6, 12, 16, 20, 33, 48, 80, 96, 100, 130, 160, 192, 320, 384, 640])
 def test_odd_dims_and_dtypes(E, O, dim, dtype):
     # feature sizes that force the 8- and 4-byte vector paths and partially filled groups;
     # integer tables must be bit-exact (wrapping adds)

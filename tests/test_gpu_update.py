@@ -130,8 +130,14 @@ def test_update_partitions(E, O):
     assert np.array_equal(A.to_numpy(), ref.data)
 
 
-@pytest.mark.parametrize("dtype,dim", [(np.float64, 24), (np.float32, 5), (np.float32, 1504), (np.float64, 130)])
+@pytest.mark.parametrize("dtype,dim", [(np.float64, 24), (np.float32, 5), (np.float32, 1504), (np.float64, 130),
+                                       # rows of 3 * 2^k / 5 * 2^k vectors: the exact-fit layouts (4..32 lanes x 3 or 5 vectors)
+                                       (np.float32, 12), (np.float32, 48), (np.float32, 96), (np.float32, 192), (np.float32, 384),
+                                       (np.float32, 20), (np.float32, 80), (np.float32, 160), (np.float32, 320), (np.float32, 640),
+                                       (np.float64, 40), (np.float16, 80)])
 def test_update_other_shapes(E, O, dtype, dim):
+    if dtype == np.float16:
+        pytest.skip("half-precision shapes are covered by test_gpu_halfprec.py")
     rng = np.random.default_rng(dim)
     base = rng.standard_normal((dim, 60)).astype(dtype)
     inds = rng.integers(1, 61, (7, 90))
