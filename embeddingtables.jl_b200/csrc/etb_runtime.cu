@@ -43,8 +43,8 @@ int32_t validate_table(const etb_table& t, const char* who) {
     ETB_REQUIRE(t.nrows >= 0, "%s: negative nrows", who);
     if (t.chunks && t.shard_rows == ETB_TABLE_CACHED) {
         const etb_cache_desc* c = (const etb_cache_desc*)t.chunks;
-        ETB_REQUIRE(t.base && c->rows && c->slot_of_row && c->row_of_slot && c->cursor && c->capacity >= 0,
-                    "%s: cached table needs base, rows, slot_of_row, row_of_slot and cursor", who);
+        ETB_REQUIRE(t.base && c->rows && c->slot_of_row && c->row_of_slot && c->cursor && c->hist && c->capacity >= 0,
+                    "%s: cached table needs base, rows, slot_of_row, row_of_slot, cursor and hist", who);
         ETB_REQUIRE(t.nrows <= 0x7fffffffll && c->capacity <= 0x7fffffffll, "%s: cached table: more than 2^31 rows / slots", who);
     } else if (t.chunks) {
         ETB_REQUIRE(t.shard_rows > 0 && t.shard_rows <= 0xffffffffll,

@@ -694,6 +694,25 @@ __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
 }
 
+// shared-memory vector load the compiler may not sink towards its use: the consumer wants U of them in flight
+template <int VB>
+__device__ __forceinline__ void lds_vec(void* out, const char* p) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    if constexpr (VB == 16) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+        *(uint4*)out = v;
+    } else if constexpr (VB == 8) {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+        *(uint2*)out = v;
+    } else {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        *(uint32_t*)out = v;
+    }
+}
+
 template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads)
 long_strict_kernel(const __grid_constant__ UpdParams P) {
@@ -709,13 +728,15 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
     constexpr int kProducers = kUThreads - 32;
     // a producer's pieces of a batch: piece pc = (tid - 32) + k * 224 is vector pv[k] of the batch's row pr[k] -- the
     // same for every batch, so the divisions happen once per kernel
-    int pr[kStrictPieces], pv[kStrictPieces];
+    int pr[kStrictPieces], pvb[kStrictPieces], poff[kStrictPieces];  // row in the batch, byte in the row, byte in the stage
 #pragma unroll
     for (int k = 0; k < kStrictPieces; ++k) {
         const int pc = (int)threadIdx.x - 32 + k * kProducers;
         pr[k] = producer ? pc / nvec : rows_per_stage;  // warp 0: no pieces
-        pv[k] = pc - pr[k] * nvec;
+        pvb[k] = (pc - pr[k] * nvec) * VB;
+        poff[k] = pr[k] * row_bytes + pvb[k];
     }
+    const bool full = G * VPL == nvec;  // every lane of the group holds VPL vectors of the row
     const uint32_t n_long = P.counters->n_long;
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
@@ -731,23 +752,22 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
         const int nbatch = (int)((stop - start + rows_per_stage - 1) / rows_per_stage);
         // producers: delta columns of my pieces' members in batch b (independent loads; issued one batch ahead of use)
         int32_t col[kStrictPieces];
+        const int32_t* bmap = P.map + start;
+        const int members = (int)(stop - start);
         auto load_map = [&](int b) {
-            const int64_t m0 = start + (int64_t)b * rows_per_stage;
-            const int rows = b < nbatch ? (int)min((int64_t)rows_per_stage, stop - m0) : 0;
+            const int rows = min(rows_per_stage, members - b * rows_per_stage);  // <= 0 past the last batch
 #pragma unroll
-            for (int k = 0; k < kStrictPieces; ++k) col[k] = pr[k] < rows ? __ldg(P.map + m0 + pr[k]) : 0;
+            for (int k = 0; k < kStrictPieces; ++k) col[k] = pr[k] < rows ? __ldg(bmap + b * rows_per_stage + pr[k]) : 0;
         };
         // producers: member rows of batch b -> stage b % kStrictStages, one VB-byte piece per thread and step
+        const char* dbase = d.delta;
+        const int64_t ldb = d.ld_delta_bytes;
         auto issue = [&](int b) {
-            if (b < nbatch) {
-                const int rows = (int)min((int64_t)rows_per_stage, stop - (start + (int64_t)b * rows_per_stage));
-                char* stage = s_rows + (size_t)(b % kStrictStages) * rows_per_stage * row_bytes;
+            const int rows = min(rows_per_stage, members - b * rows_per_stage);
+            char* stage = s_rows + (b % kStrictStages) * (rows_per_stage * row_bytes);
 #pragma unroll
-                for (int k = 0; k < kStrictPieces; ++k)
-                    if (pr[k] < rows)
-                        cp_async<VB>(stage + (size_t)pr[k] * row_bytes + pv[k] * VB,
-                                     d.delta + (int64_t)col[k] * d.ld_delta_bytes + pv[k] * VB);
-            }
+            for (int k = 0; k < kStrictPieces; ++k)
+                if (pr[k] < rows) cp_async<VB>(stage + poff[k], dbase + (int64_t)col[k] * ldb + pvb[k]);
             asm volatile("cp.async.commit_group;" ::: "memory");  // one group per batch, empty ones included
         };
         A acc[VPL];
@@ -776,25 +796,25 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
             issue(b + kStrictStages - 1);     // with the columns loaded one iteration ago
             load_map(b + kStrictStages);      // in flight until the next iteration
             if (consumer) {
-                const int rows = (int)min((int64_t)rows_per_stage, stop - (start + (int64_t)b * rows_per_stage));
-                const char* stage = s_rows + (size_t)(b % kStrictStages) * rows_per_stage * row_bytes;
+                const int rows = min(rows_per_stage, members - b * rows_per_stage);
+                const char* stage = s_rows + (b % kStrictStages) * (rows_per_stage * row_bytes);
                 // U rows from shared memory into registers, then their additions in order: the shared-memory latency is
                 // paid once per U rows instead of once per row
                 constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
                 const char* mine_s = stage + (size_t)gl * VB;
                 int r = 0;
-                for (; r + U <= rows; r += U) {
-                    V v[U][VPL];
+                if (full) {  // no lane predicates: U * VPL independent loads, then the ordered additions
+                    for (; r + U <= rows; r += U) {
+                        V v[U][VPL];
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
+                        for (int u = 0; u < U; ++u)
 #pragma unroll
-                        for (int p = 0; p < VPL; ++p)
-                            if (on[p]) v[u][p] = *(const V*)(mine_s + (size_t)(r + u) * row_bytes + (size_t)p * G * VB);
+                            for (int p = 0; p < VPL; ++p) lds_vec<VB>(&v[u][p], mine_s + (r + u) * row_bytes + p * G * VB);
 #pragma unroll
-                    for (int u = 0; u < U; ++u)
+                        for (int u = 0; u < U; ++u)
 #pragma unroll
-                        for (int p = 0; p < VPL; ++p)
-                            if (on[p]) acc_add(acc[p], v[u][p]);
+                            for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[u][p]);
+                    }
                 }
                 for (; r < rows; ++r) {
 #pragma unroll
@@ -1141,6 +1161,7 @@ struct CacheItem {
     int32_t* slot_of_row;
     int32_t* row_of_slot;
     int32_t* cursor;
+    int32_t* hist;
     int64_t row_stride, row_bytes;
     int32_t capacity, pad;
 };
@@ -1152,7 +1173,38 @@ struct CacheParams {
     int32_t row_bits, min_count, n_items;
 };
 
+// occurrence counts (clamped to the last bin) of the rows of host-tier tables that are not cached yet
+__global__ void __launch_bounds__(256) cache_count_kernel(const __grid_constant__ CacheParams P) {
+    const int64_t nnz = *P.nnz;
+    for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < nnz; b += (int64_t)gridDim.x * 256) {
+        const BucketRec rec = P.recs[b];
+        const int slot_id = (int)(rec.key >> P.row_bits);
+        if (slot_id >= P.n_items || !P.item[slot_id].slot_of_row) continue;
+        const CacheItem& c = P.item[slot_id];
+        const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+        if (c.slot_of_row[rec.key & row_mask] >= 0) continue;
+        const int64_t stop = (b + 1 < nnz) ? (int64_t)P.recs[b + 1].start : P.n_total;
+        atomicAdd(c.hist + (int)min((int64_t)ETB_CACHE_HIST_BINS - 1, stop - (int64_t)rec.start), 1);
+    }
+}
+
+// the smallest count t >= min_count such that the uncached rows with >= t occurrences fit into the free slots
+__device__ __forceinline__ int cache_threshold(const CacheItem& c, int min_count) {
+    const int free_slots = c.capacity - min(*c.cursor, c.capacity);
+    int t = ETB_CACHE_HIST_BINS - 1, fit = 0;
+    for (int k = ETB_CACHE_HIST_BINS - 1; k >= min_count; --k) {
+        fit += c.hist[k];
+        if (fit > free_slots) break;
+        t = k;
+    }
+    return t;
+}
+
 __global__ void __launch_bounds__(256) cache_admit_kernel(const __grid_constant__ CacheParams P) {
+    __shared__ int s_threshold[kUMaxItems];
+    for (int i = threadIdx.x; i < P.n_items; i += 256)
+        s_threshold[i] = P.item[i].slot_of_row ? cache_threshold(P.item[i], P.min_count) : 0x7fffffff;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t nnz = *P.nnz;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
@@ -1165,7 +1217,7 @@ __global__ void __launch_bounds__(256) cache_admit_kernel(const __grid_constant_
         const int64_t stop = (b + 1 < nnz) ? (int64_t)P.recs[b + 1].start : P.n_total;
         const int64_t row = (int64_t)(rec.key & row_mask);
         int s = -1;
-        if (lane == 0 && stop - (int64_t)rec.start >= P.min_count && c.slot_of_row[row] < 0) {
+        if (lane == 0 && stop - (int64_t)rec.start >= s_threshold[slot_id] && c.slot_of_row[row] < 0) {
             s = atomicAdd(c.cursor, 1);
             if (s >= c.capacity) {  // full: undo (the cursor never runs away)
                 atomicSub(c.cursor, 1);
@@ -1212,6 +1264,7 @@ static bool make_cache_item(const etb_table& t, CacheItem& c) {
     c.slot_of_row = d->slot_of_row;
     c.row_of_slot = d->row_of_slot;
     c.cursor = d->cursor;
+    c.hist = d->hist;
     c.row_stride = (int64_t)t.ld * (int64_t)elt_bytes(t.elt);
     c.row_bytes = (int64_t)t.dim * (int64_t)elt_bytes(t.elt);
     c.capacity = (int32_t)d->capacity;
@@ -1332,7 +1385,11 @@ int32_t etb_cache_admit(const etb_index_view* view_host, const etb_update_item* 
         P.row_bits = view_host->row_bits;
         P.min_count = std::max(1, min_count);
         P.n_items = n;
+        for (int j = 0; j < n; ++j)
+            if (P.item[j].hist) ETB_CUDA(cudaMemsetAsync(P.item[j].hist, 0, ETB_CACHE_HIST_BINS * sizeof(int32_t), (cudaStream_t)stream));
         const int grid = (int)std::min<int64_t>((view_host->n_total + 7) / 8, (int64_t)num_sms() * 8);
+        cache_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        ETB_LAUNCHED();
         cache_admit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
         ETB_LAUNCHED();
     }

@@ -11,8 +11,9 @@ addresses it directly over PCIe, and up to `cache_rows` of its rows have a copy 
   * Forward context: a pure read through that rule.
   * Update context: update! writes a cached row in HBM (it is authoritative there until `flush()`), an uncached row on
     the host; afterwards -- still the Update phase -- `etb_cache_admit` walks the bucket records that index! just
-    produced and gives every row that the batch touched at least `min_count` times a free slot (hot Zipf rows arrive
-    first; nothing is evicted, `flush()` + `clear()` start over).
+    produced: it histograms the occurrence counts of the rows still on the host and admits those at or above the
+    count at which they fit into the free slots, never below `min_count` (the hottest rows of a Zipf batch come first;
+    nothing is evicted, `flush()` + `clear()` start over).
 
 Arithmetic does not depend on where a row lives: results equal the all-HBM tables' bit for bit
 (tests/test_gpu_cached.py).
@@ -31,7 +32,7 @@ from .tables import AbstractEmbeddingTable, ArgumentError, Dynamic, Forward, Ind
 
 class CacheDesc(C.Structure):   # etb_cache_desc (a host struct of device pointers)
     _fields_ = [("rows", C.c_void_p), ("slot_of_row", C.c_void_p), ("row_of_slot", C.c_void_p),
-                ("cursor", C.c_void_p), ("capacity", C.c_int64)]
+                ("cursor", C.c_void_p), ("capacity", C.c_int64), ("hist", C.c_void_p)]
 
 
 TABLE_CACHED = -1   # ETB_TABLE_CACHED
@@ -58,8 +59,9 @@ class CachedEmbedding(AbstractEmbeddingTable):
         self._slot_of_row = torch.full((max(1, n),), -1, dtype=torch.int32, device="cuda")
         self._row_of_slot = torch.zeros(max(1, self.capacity), dtype=torch.int32, device="cuda")
         self._cursor = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self._hist = torch.zeros(64, dtype=torch.int32, device="cuda")      # ETB_CACHE_HIST_BINS
         self._desc = CacheDesc(self.cache.ptr, self._slot_of_row.data_ptr(), self._row_of_slot.data_ptr(),
-                               self._cursor.data_ptr(), self.capacity)
+                               self._cursor.data_ptr(), self.capacity, self._hist.data_ptr())
         self.context = None     # the IndexingContext of the last descriptor() request (introspection / tests)
 
     def size(self, d=None):

@@ -207,16 +207,17 @@ def index_(indexer: Indexer, tables, grads):
 
 
 # ------------------------------------------------------------------------------ update!
-# Reduction order of update!.  "strict": every bucket is accumulated strictly in occurrence order
-# like the reference (bit-identical to it).  "split": buckets with more than 128 members (hot
-# Zipf rows) are summed as 128-member chunks combined in chunk order -- deterministic and
-# atomics-free, but a different association (within the north star's 1e-5 tolerance); buckets of
-# up to 128 members are identical in both modes.
-_ORDER = {"mode": "split"}
+# Reduction order of update!.  "strict" (the default): every bucket is accumulated strictly in occurrence order
+# like the reference (bit-identical to it); a bucket of more than 128 members is streamed through shared memory by
+# one CTA (long_strict_kernel).  "split": such buckets (hot Zipf rows) are summed as 128-member chunks combined in
+# chunk order -- deterministic and atomics-free, but a different association (within the north star's 1e-5
+# tolerance); buckets of up to 128 members are identical in both modes.
+DEFAULT_ORDER = "strict"
+_ORDER = {"mode": DEFAULT_ORDER}
 
 
 def set_update_order(mode: str):
-    """'split' (default) or 'strict' (bit-identical to the reference's sequential accumulation)."""
+    """'strict' (default: bit-identical to the reference's sequential accumulation) or 'split'."""
     if mode not in ("split", "strict"):
         raise ValueError(mode)
     _ORDER["mode"] = mode

@@ -108,8 +108,9 @@ typedef struct etb_table {
  * that the GPU can address (`base`); `rows` caches up to `capacity` of its rows in HBM and `slot_of_row` says which.
  * Every kernel resolves a row as  slot_of_row[i-1] >= 0 ? rows + slot*ld : base + (i-1)*ld,  so results are bit for
  * bit those of an all-HBM table.  A cached row is authoritative in HBM (update! writes it there) until
- * etb_cache_flush copies it back.  etb_cache_admit, run after update! (the Update phase), admits the rows that the
- * batch touched at least `min_count` times while slots are free.
+ * etb_cache_flush copies it back.  etb_cache_admit, run after update! (the Update phase), admits the rows the batch
+ * touched most often: it histograms the occurrence counts of the rows that are still on the host and admits those at
+ * or above the count at which they fit into the free slots (never below `min_count`).
  */
 #define ETB_TABLE_CACHED (-1)
 typedef struct etb_cache_desc { /* a HOST struct of DEVICE pointers */
@@ -118,7 +119,9 @@ typedef struct etb_cache_desc { /* a HOST struct of DEVICE pointers */
     int32_t* row_of_slot;  /* capacity entries: 0-based row held by each slot in use        */
     int32_t* cursor;       /* one int32: slots in use                                       */
     int64_t capacity;
+    int32_t* hist;         /* ETB_CACHE_HIST_BINS int32 of scratch for etb_cache_admit       */
 } etb_cache_desc;
+#define ETB_CACHE_HIST_BINS 64
 
 /*
  * One table's share of an ensemble lookup: replaces one `lookup!(out[i], x[i], I[i])`

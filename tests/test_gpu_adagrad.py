@@ -57,7 +57,7 @@ def test_adagrad_steps_match_oracle(E, O, name, dim, order):
                 assert np.array_equal(_bits(table.to_numpy()), _bits(want)), (name, dim, static, step)
                 assert np.array_equal(_bits(opt.state(table).numpy()), _bits(state)), (name, dim, static, step)
     finally:
-        E.set_update_order("split")
+        E.set_update_order("strict")
 
 
 def test_adagrad_ensemble_and_hot_rows(E, O):
@@ -83,7 +83,7 @@ def test_adagrad_ensemble_and_hot_rows(E, O):
                 assert np.array_equal(_bits(got), _bits(want)) and np.array_equal(_bits(gstate), _bits(state))
             else:
                 assert np.allclose(got, want, rtol=1e-5, atol=1e-6) and np.allclose(gstate, state, rtol=1e-5)
-    E.set_update_order("split")
+    E.set_update_order("strict")
 
 
 def test_adagrad_rejects_long_rows(E):

@@ -20,10 +20,11 @@ def O():
 
 
 def zipf(rng, nrows, n, alpha=1.05):
+    """Zipf(alpha) ranks; rank -> row through ONE fixed permutation, so that the hot rows stay hot from batch to batch"""
     w = 1.0 / np.arange(1, nrows + 1, dtype=np.float64) ** alpha
     cdf = np.cumsum(w)
     cdf /= cdf[-1]
-    return rng.permutation(nrows)[np.searchsorted(cdf, rng.random(n))] + 1
+    return np.random.default_rng(nrows).permutation(nrows)[np.searchsorted(cdf, rng.random(n))] + 1
 
 
 @pytest.mark.parametrize("dim,static", [(128, True), (64, False), (20, False)])

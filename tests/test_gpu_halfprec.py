@@ -98,7 +98,7 @@ def test_update(E, O, which, dim, order):
                 want = O.update_lowp(base.copy(order="F"), delta, I, 0.37)
                 assert np.array_equal(_bits(table.to_numpy()), _bits(want)), (dim, static, shape)
     finally:
-        E.set_update_order("split")
+        E.set_update_order("strict")
 
 
 @pytest.mark.parametrize("which", [0, 1])
@@ -123,7 +123,7 @@ def test_update_hot_rows(E, O, which):
             g, w = got.astype(np.float32), want.astype(np.float32)
             eps = 2.0 ** -10 if dt == np.float16 else 2.0 ** -7          # one unit in the last place, relative
             assert np.all(np.abs(g - w) <= eps * np.maximum(np.abs(w), 1e-3))
-    E.set_update_order("split")
+    E.set_update_order("strict")
 
 
 @pytest.mark.parametrize("which", [0, 1])

@@ -118,4 +118,4 @@ def test_random_update(E, O, seed, order):
                 if (~short).any():
                     assert np.linalg.norm(got - r.data) <= 1e-5 * np.linalg.norm(r.data)
     finally:
-        E.set_update_order("split")
+        E.set_update_order("strict")

@@ -23,7 +23,7 @@ def order(request, E):
     members; every reference-shaped test stays below that, so `==` holds in both."""
     E.set_update_order(request.param)
     yield request.param
-    E.set_update_order("split")
+    E.set_update_order("strict")   # the default
 
 
 @pytest.fixture(scope="module")

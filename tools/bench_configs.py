@@ -153,7 +153,7 @@ def config_c3(fh):
                   "frac_of_measured_peak_graph": bytes_alg / tg / 1e6 / PEAK,
                   "lookups_per_sec": n / (t * 1e-3), "algorithmic_bytes": bytes_alg, "gbs": bytes_alg / t / 1e6,
                   "frac_of_measured_peak": bytes_alg / t / 1e6 / PEAK}, fh)
-        E.set_update_order("split")
+        E.set_update_order("strict")
 
 
 def config_c5(fh, quick=False):

@@ -13,7 +13,7 @@ I = E.DeviceArray.from_numpy(zipf_indices(rng, nrows, n))
 delta = E.DeviceArray(torch.randn(dim * n, device="cuda"), (dim, n))
 grad = E.SparseEmbeddingUpdate(E.Static(dim), delta, I)
 ix, opt = E.Indexer(), E.Descent(0.01)
-E.set_update_order(os.environ.get("ETB_ORDER", "split"))
+E.set_update_order(os.environ.get("ETB_ORDER", "strict"))
 for _ in range(4):
     E.update_(opt, table, grad, ix)
 torch.cuda.synchronize()

@@ -41,7 +41,7 @@ for dtype, dim in [(np.float32, 128), (np.float32, 5), (np.float64, 24), (np.int
                 for s in range(1, 4):
                     E.update_table_(table, g, E.IndexerView(ix, 3, s), 0.1)
                 E.uncompress(g, nrows)
-            E.set_update_order("split")
+            E.set_update_order("strict")
 tables = [E.SimpleEmbedding(rng.standard_normal((d, 90)).astype(np.float32)) for d in (16, 64, 5, 128)]
 I = [rng.integers(1, 91, (4, 37)) for _ in tables]
 out, back = E.pullback(E.maplookup, E.PreallocationStrategy(3), tables, I)
