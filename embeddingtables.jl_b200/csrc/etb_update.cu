@@ -750,24 +750,26 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
         const UpdDesc& d = P.item[slot];
         char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
         const int nbatch = (int)((stop - start + rows_per_stage - 1) / rows_per_stage);
-        // producers: delta columns of my pieces' members in batch b (independent loads; issued one batch ahead of use)
-        int32_t col[kStrictPieces];
+        // producers: delta columns of my pieces' members in batch b.  The loads are issued kMapAhead batches before
+        // the batch is requested (a ring of register sets): one iteration is shorter than a load's round trip
+        constexpr int kMapAhead = 4;
+        int32_t col[kMapAhead][kStrictPieces];
         const int32_t* bmap = P.map + start;
         const int members = (int)(stop - start);
-        auto load_map = [&](int b) {
+        auto load_map = [&](int b, int32_t (&c)[kStrictPieces]) {
             const int rows = min(rows_per_stage, members - b * rows_per_stage);  // <= 0 past the last batch
 #pragma unroll
-            for (int k = 0; k < kStrictPieces; ++k) col[k] = pr[k] < rows ? __ldg(bmap + b * rows_per_stage + pr[k]) : 0;
+            for (int k = 0; k < kStrictPieces; ++k) c[k] = pr[k] < rows ? __ldg(bmap + b * rows_per_stage + pr[k]) : 0;
         };
         // producers: member rows of batch b -> stage b % kStrictStages, one VB-byte piece per thread and step
         const char* dbase = d.delta;
         const int64_t ldb = d.ld_delta_bytes;
-        auto issue = [&](int b) {
+        auto issue = [&](int b, const int32_t (&c)[kStrictPieces]) {
             const int rows = min(rows_per_stage, members - b * rows_per_stage);
             char* stage = s_rows + (b % kStrictStages) * (rows_per_stage * row_bytes);
 #pragma unroll
             for (int k = 0; k < kStrictPieces; ++k)
-                if (pr[k] < rows) cp_async<VB>(stage + poff[k], dbase + (int64_t)col[k] * ldb + pvb[k]);
+                if (pr[k] < rows) cp_async<VB>(stage + poff[k], dbase + (int64_t)c[k] * ldb + pvb[k]);
             asm volatile("cp.async.commit_group;" ::: "memory");  // one group per batch, empty ones included
         };
         A acc[VPL];
@@ -785,17 +787,21 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
             state = (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask);
             st_old = *state;
         }
-        for (int b = 0; b < kStrictStages - 1; ++b) {
-            load_map(b);
-            issue(b);
+        for (int b = 0; b < kStrictStages - 1; ++b) {  // the first stages: request as soon as the columns are here
+            load_map(b, col[0]);
+            issue(b, col[0]);
         }
-        load_map(kStrictStages - 1);
-        for (int b = 0; b < nbatch; ++b) {
+#pragma unroll
+        for (int q = 0; q < kMapAhead; ++q) load_map(kStrictStages - 1 + q, col[q]);
+        for (int b0 = 0; b0 < nbatch; b0 += kMapAhead) {
+#pragma unroll
+          for (int q = 0; q < kMapAhead; ++q) {  // batch b0 + q; every thread runs all kMapAhead steps (barriers)
+            const int b = b0 + q;
             asm volatile("cp.async.wait_group %0;" ::"n"(kStrictStages - 2) : "memory");  // my pieces of batch b have landed
             __syncthreads();  // everybody's have; the stage of batch b - 1 is free again
-            issue(b + kStrictStages - 1);     // with the columns loaded one iteration ago
-            load_map(b + kStrictStages);      // in flight until the next iteration
-            if (consumer) {
+            issue(b + kStrictStages - 1, col[q]);                     // columns loaded kMapAhead steps ago
+            load_map(b + kStrictStages - 1 + kMapAhead, col[q]);      // in flight for the next kMapAhead steps
+            if (consumer && b < nbatch) {
                 const int rows = min(rows_per_stage, members - b * rows_per_stage);
                 const char* stage = s_rows + (b % kStrictStages) * (rows_per_stage * row_bytes);
                 // U rows from shared memory into registers, then their additions in order: the shared-memory latency is
@@ -826,6 +832,7 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
                     }
                 }
             }
+          }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (consumer) {
@@ -849,6 +856,177 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
             }
         }
         __syncthreads();  // the stages are reused by the next bucket
+    }
+}
+
+// The same job with Blackwell's bulk-copy engine (rows of 16-byte vectors): warp 1 asks the TMA unit for one member
+// row per lane -- cp.async.bulk, 32 rows = one stage, completion counted in bytes on the stage's mbarrier -- and
+// warp 0 adds the rows of a stage once its barrier has flipped, then hands the stage back through a second
+// mbarrier.  No thread copies data or computes piece addresses; 6 stages of 32 rows (up to 80 KB) are in flight.
+// MEASURED SLOWER than the cp.async kernel above (C3: 2.08 vs 1.01 ms): a bulk request per 512-byte row pays the
+// copy engine's per-request cost 45 000 times.  Kept behind ETB_STRICT_BULK=1 as the evidence.
+constexpr int kBulkStages = 6, kBulkRows = 32, kBulkThreads = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <typename T, int VPL, int OPT>
+__global__ void __launch_bounds__(kBulkThreads)
+long_strict_bulk_kernel(const __grid_constant__ UpdParams P) {
+    constexpr int VB = 16;
+    using V = Vec<T, VB>;
+    using A = AccVec<T, VB>;
+    extern __shared__ __align__(128) char s_rows[];  // [kBulkStages][kBulkRows][row_bytes]
+    __shared__ __align__(8) uint64_t s_full[kBulkStages], s_empty[kBulkStages];
+    const int G = P.G, nvec = P.nvec;
+    const int row_bytes = nvec * VB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1);
+    const bool adder = warp == 0 && lane < G;  // group 0 = the first G lanes of warp 0
+    const bool full = G * VPL == nvec;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < kBulkStages; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_empty[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t n_long = P.counters->n_long;
+    const int64_t nnz = *P.nnz;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    const acc_t<T> eta = (acc_t<T>)P.eta;
+    uint32_t it = 0;  // batches handled so far by this CTA (both warps count alike): stage = it % S, use = it / S
+    for (uint32_t j = blockIdx.x; j < n_long; j += gridDim.x) {
+        const LongRec lr = P.longs[j];
+        const BucketRec rec = P.recs[lr.bucket];
+        const int64_t start = rec.start;
+        const int64_t stop = ((int64_t)lr.bucket + 1 < nnz) ? (int64_t)P.recs[lr.bucket + 1].start : P.n_total;
+        const int slot = (int)(rec.key >> P.row_bits) - P.slot0;
+        const UpdDesc& d = P.item[slot];
+        const int members = (int)(stop - start);
+        const int nbatch = (members + kBulkRows - 1) / kBulkRows;
+        if (warp == 1) {
+            // ---- producer: one member row per lane and batch; the delta column of the next batch is fetched while
+            // this one is issued
+            const int32_t* bmap = P.map + start;
+            constexpr int kAhead = 8;  // the delta column of a batch is fetched 8 batches before it is requested
+            int32_t col[kAhead];
+#pragma unroll
+            for (int q = 0; q < kAhead; ++q) col[q] = q * kBulkRows + lane < members ? __ldg(bmap + q * kBulkRows + lane) : 0;
+            for (int b0 = 0; b0 < nbatch; b0 += kAhead) {
+#pragma unroll
+                for (int q = 0; q < kAhead; ++q) {
+                    const int b = b0 + q;
+                    if (b < nbatch) {
+                        const uint32_t stage = it % kBulkStages, use = it / kBulkStages;
+                        const int rows = min(kBulkRows, members - b * kBulkRows);
+                        if (use > 0) mbar_wait(&s_empty[stage], (use - 1) & 1u);  // the adders are done with this stage
+                        if (lane == 0) mbar_expect_tx(&s_full[stage], (uint32_t)(rows * row_bytes));
+                        __syncwarp();
+                        if (lane < rows)
+                            bulk_g2s(s_rows + ((size_t)stage * kBulkRows + lane) * row_bytes,
+                                     d.delta + (int64_t)col[q] * d.ld_delta_bytes, (uint32_t)row_bytes, &s_full[stage]);
+                        const int nxt = (b + kAhead) * kBulkRows + lane;
+                        col[q] = nxt < members ? __ldg(bmap + nxt) : 0;
+                        ++it;
+                    }
+                }
+            }
+        } else {
+            // ---- consumer: the member rows of a stage, added in order
+            char* row = const_cast<char*>(row_ptr(d.table, (int64_t)(rec.key & row_mask) + 1));
+            A acc[VPL];
+            V old[VPL];
+            acc_t<T> st_old = acc_t<T>(0);
+            acc_t<T>* state = nullptr;
+            bool on[VPL];
+#pragma unroll
+            for (int p = 0; p < VPL; ++p) {
+                acc_fill(acc[p], acc_t<T>(0));  // accum = zero, then += members in order
+                on[p] = adder && gl + p * G < nvec;
+                if (on[p]) ld_plain<VB>(&old[p], row + (size_t)(gl + p * G) * VB);
+            }
+            if (OPT == kOptAdagrad && adder) {
+                state = (acc_t<T>*)P.state[slot] + (int64_t)(rec.key & row_mask);
+                st_old = *state;
+            }
+            for (int b = 0; b < nbatch; ++b, ++it) {
+                const uint32_t stage = it % kBulkStages, use = it / kBulkStages;
+                const int rows = min(kBulkRows, members - b * kBulkRows);
+                mbar_wait(&s_full[stage], use & 1u);  // the bytes of this stage have landed
+                if (adder) {
+                    constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
+                    const char* mine_s = s_rows + (size_t)stage * kBulkRows * row_bytes + (size_t)gl * VB;
+                    int r = 0;
+                    if (full) {
+                        for (; r + U <= rows; r += U) {
+                            V v[U][VPL];
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+#pragma unroll
+                                for (int p = 0; p < VPL; ++p) lds_vec<VB>(&v[u][p], mine_s + (r + u) * row_bytes + p * G * VB);
+#pragma unroll
+                            for (int u = 0; u < U; ++u)
+#pragma unroll
+                                for (int p = 0; p < VPL; ++p) acc_add(acc[p], v[u][p]);
+                        }
+                    }
+                    for (; r < rows; ++r) {
+#pragma unroll
+                        for (int p = 0; p < VPL; ++p) {
+                            if (on[p]) {
+                                V v;
+                                lds_vec<VB>(&v, mine_s + r * row_bytes + p * G * VB);
+                                acc_add(acc[p], v);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[stage]);  // the stage may be refilled
+            }
+            if (adder) {
+                if constexpr (OPT == kOptSgd) {
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p) {
+                        if (on[p]) {
+                            V out;
+#pragma unroll
+                            for (int k = 0; k < V::NE; ++k) out.e[k] = sgd_apply<T>(old[p].e[k], acc[p].e[k], eta, d.table.pad != 0);
+                            st_plain<VB>(row + (size_t)(gl + p * G) * VB, &out);
+                        }
+                    }
+                } else {
+                    V out[VPL];
+                    adagrad_apply<T, VB, VPL>(out, old, acc, on, state, st_old, eta, (acc_t<T>)P.eps, nvec * V::NE, G, gl,
+                                              group_mask(G, lane));
+#pragma unroll
+                    for (int p = 0; p < VPL; ++p)
+                        if (on[p]) st_plain<VB>(row + (size_t)(gl + p * G) * VB, &out[p]);
+                }
+            }
+        }
     }
 }
 
@@ -898,7 +1076,18 @@ template <typename T, int VB, int VPL, int OPT>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain) sgd_update_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
     else if (which == kKernelTasks) bucket_tasks_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
-    else if (which == kKernelStrictLong) {
+    else if (which == kKernelStrictLong && VB == 16 && P.nvec * VB * kBulkRows * kBulkStages <= 200 * 1024 &&
+             getenv("ETB_STRICT_BULK")) {  // measured 2x slower than the cp.async variant for 512-byte rows: opt-in only
+        if constexpr (VB == 16) {  // the bulk-copy (TMA) variant
+            const int smem = P.nvec * VB * kBulkRows * kBulkStages;
+            static thread_local int configured = 0;
+            if (smem > configured) {
+                cudaFuncSetAttribute(long_strict_bulk_kernel<T, VPL, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                configured = smem;
+            }
+            long_strict_bulk_kernel<T, VPL, OPT><<<grid, kBulkThreads, smem, s>>>(P);
+        }
+    } else if (which == kKernelStrictLong) {
         constexpr int kSmem = kStrictStages * kStrictStageBytes;  // 96 KB of dynamic shared memory: opt in once
         static thread_local bool configured = false;
         if (!configured) {
