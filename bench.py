@@ -398,13 +398,14 @@ def run_ours(args):
     kernels = {
         "pooled_kernel": {"ms": fwd_ms, "bytes": fwd_bytes, "gbs": fwd_bytes / fwd_ms / 1e6},
         "sgd_update_kernel": {"ms": upd_ms, "bytes": upd_kernel_bytes, "gbs": upd_kernel_bytes / upd_ms / 1e6},
-        "index(make_pairs+radix sort+select)": {"ms": index_ms},
+        "index(segmented radix sort: 2 x (hist, scan, scatter) + bucket records)": {"ms": index_ms},
     }
     dom = "pooled_kernel" if fwd_ms >= upd_ms else "sgd_update_kernel"
-    traffic = None      # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")) as f:
-            traffic = json.load(f)["kernels"][dom]["dram_bytes"] if args.dist == "uniform" else None
+    traffic = None      # DRAM bytes per launch of that kernel from the newest committed ncu --set full capture
+    try:                # (profiles/r2_ncu_kernels.json, regenerated by tools/final_n1.sh whenever a kernel changes)
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_kernels.json")) as f:
+            key = {"sgd_update_kernel": "sgd_update_exact_kernel", "pooled_kernel": "pooled_kernel"}[dom]
+            traffic = json.load(f)["kernels"][key]["dram_bytes"] if args.dist == "uniform" else None
     except Exception:
         traffic = None
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",

@@ -12,6 +12,7 @@ from __future__ import annotations
 import ctypes as C
 
 import numpy as np
+import torch
 
 from . import _lib
 from .darray import DeviceArray, as_device_indices, current_stream_ptr
@@ -116,8 +117,8 @@ class SimpleParallelStrategy(AbstractExecutionStrategy):
 class PreallocationStrategy(AbstractExecutionStrategy):
     """PreallocationStrategy{T}(prependrows): fuse the lookups with the concatenation
     (src/lookup.jl:284-291).  `eltype` = the {T} override of the output element type
-    (`_select_eltype`, :293-294); it must equal the tables' eltype on this path (the kernels do
-    not convert)."""
+    (`_select_eltype`, :293-294); when it differs from the tables' eltype the lookups are
+    converted into the output matrix after the kernel (see maplookup_)."""
 
     def __init__(self, prependrows: int = 0, eltype=None):
         self.prependrows = int(prependrows)
@@ -152,6 +153,18 @@ def maplookup_(strategy: AbstractExecutionStrategy, out, x, I0, worksize_div: in
     if len(I) != len(x):
         raise ValueError(f"{len(x)} tables but {len(I)} index arrays")
     items = []
+    if isinstance(strategy, PreallocationStrategy) and x and out.dtype != x[0].dtype:
+        # PreallocationStrategy{U} with U != eltype(tables) (`_select_eltype`, src/lookup.jl:293-294, 312): the kernels
+        # write the tables' element type, so the lookups land in a scratch matrix of that type and are converted into
+        # `out` below its prepend rows.  Exact for non-reducing lookups (convert(U, x)); a pooled sum is formed in the
+        # tables' type and converted once, where the reference's generic path would accumulate in promote_type(U, T).
+        rows = sum(featuresize(t) for t in x)
+        batch = _batchsize(I)
+        tmp = example(x).similar(x[0].dtype, (rows, batch))
+        maplookup_(PreallocationStrategy(0), tmp, x, I)
+        view = torch.as_strided(out.buf, (batch, rows), (out.ld, 1), out.offset + strategy.prependrows)
+        view.copy_(tmp.buf[tmp.offset:tmp.offset + rows * batch].view(batch, rows))
+        return out
     if isinstance(strategy, PreallocationStrategy):
         off = strategy.prependrows
         batch = _batchsize(I)

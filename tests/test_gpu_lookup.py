@@ -325,3 +325,21 @@ def test_strided_upload_download_of_row_slices(E):
     assert np.array_equal(back[2:18], dense) and np.all(back[:2] == -7.0) and np.all(back[18:] == -7.0)
     with pytest.raises(AssertionError):
         dev.rows(0, 8).upload(host[::2][:8])                 # not a row-slice view
+
+
+def test_preallocation_eltype_override(E, O):
+    # PreallocationStrategy{U}(prependrows) with U != eltype(tables) (reference src/lookup.jl:293-294, 312): the output
+    # matrix has element type U; a non-reducing lookup is convert(U, x) exactly, a pooled sum is the tables'-type sum
+    # converted once; the prepend rows stay the caller's
+    rng = np.random.default_rng(77)
+    base = [rng.standard_normal((32, 200)).astype(np.float32) for _ in range(3)]
+    tables = [E.SimpleEmbedding(b, E.Static(32)) for b in base]
+    refs = [O.Table(b, static=True) for b in base]
+    for I in (rng.integers(1, 201, (50, 3)), rng.integers(1, 201, (6, 50, 3))):
+        out = E.maplookup(E.PreallocationStrategy(4, eltype=np.float64), tables, I)
+        assert out.dtype == np.float64 and out.shape == (4 + 96, 50)
+        want = O.maplookup("preallocation", refs, I, prependrows=4, out=np.zeros((100, 50), np.float32, order="F"))
+        assert np.array_equal(out.numpy()[4:], want[4:].astype(np.float64))
+    pre = E.DeviceArray.from_numpy(np.full((100, 50), -3.0, np.float64))
+    E.maplookup_(E.PreallocationStrategy(4, eltype=np.float64), pre, tables, rng.integers(1, 201, (50, 3)))
+    assert np.all(pre.numpy()[:4] == -3.0)
