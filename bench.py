@@ -276,19 +276,28 @@ def run_ours(args):
 
     # e2e: every step copies ITS indices and cotangent in from pinned host memory and its feature
     # matrix out.  Across steps the only pipelining is the standard input double buffer: step k+1's
-    # indices are uploaded on a copy stream while step k's result is downloaded (H2D and D2H use
-    # different copy engines).  Within a step the dependency chain is kept -- forward -> result on the
-    # host -> cotangent from the host -> update -- and pipelined at its two PCIe legs:
+    # indices are uploaded on the H2D stream while step k is in flight.  Within a step the dependency
+    # chain is kept PER SAMPLE (= per column of the feature matrix; what a DLRM's per-sample loss gives):
+    # forward of column j -> column j of the result on the host -> column j of the cotangent from the
+    # host -> update! of a table once ALL columns of its cotangent rows are in HBM.  PCIe is full duplex
+    # (tools/pcie_probe.py: 55 GB/s one way, 2 x 46 GB/s both ways at once), so the schedule keeps both
+    # directions busy:
     #   * the forward runs in E2E_CHUNKS column chunks, chunk c going to the host while chunk c+1 is looked up;
-    #   * the cotangent comes in as E2E_GROUPS row slices (one group of tables each, a strided 2-D copy), and
-    #     each group's update! (its own Indexer, index! prefetched beside the forward) runs as soon as its
-    #     slice has landed, while the next slice is still on the wire.
+    #   * the cotangent of the first E2E_DENSE column chunks comes in as whole column chunks (contiguous),
+    #     each as soon as ITS result chunk has reached the host -- beside the later result chunks' D2H;
+    #   * the remaining columns come in as E2E_GROUPS row slices (one group of tables each, a strided 2-D
+    #     copy), and each group's update! (its own Indexer, index! prefetched beside the forward) runs as
+    #     soon as its slice has landed, while the next slice is still on the wire.
+    # ETB_E2E_DUPLEX=0 is round 1's schedule: the whole result on the host before any cotangent is sent.
     copy_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
-    E2E_CHUNKS = 4
+    DUPLEX = os.environ.get("ETB_E2E_DUPLEX", "1") != "0"
+    E2E_CHUNKS = max(1, int(os.environ.get("ETB_E2E_CHUNKS", "8" if DUPLEX else "4")))
+    E2E_DENSE = min(E2E_CHUNKS - 1, max(0, int(os.environ.get("ETB_E2E_DENSE", str(E2E_CHUNKS // 2))))) if DUPLEX else 0
     E2E_GROUPS = max(1, min(NT, int(os.environ.get("ETB_E2E_GROUPS", "13"))))
     bounds = [round(g * NT / E2E_GROUPS) for g in range(E2E_GROUPS + 1)]
     groups = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
     group_ix = [E.Indexer() for _ in groups]
+    cb = [c * BATCH // E2E_CHUNKS for c in range(E2E_CHUNKS + 1)]
     I_buf = [I_dev, E.DeviceArray.empty((BAG, BATCH, NT), np.int64)]
     Is_buf = [Is, list(E.colwrap(I_buf[1]))]
     idx_ready = [None, None]
@@ -312,24 +321,33 @@ def run_ours(args):
         idx_ready[slot] = None
         for (a, b), ix in zip(groups, group_ix):          # side stream: overlaps forward + PCIe copies
             E.prefetch_index(ix, tables[a:b], Is_buf[slot][a:b])
+        if DUPLEX:
+            upload_indices(1 - slot)                      # next step's indices: first in the H2D queue, beside the forward
         # forward in E2E_CHUNKS column chunks: chunk c's result goes to the host (D2H stream) while chunk
-        # c+1 is being looked up
+        # c+1 is being looked up; the cotangent of a dense chunk follows its result chunk (H2D stream)
         for c in range(E2E_CHUNKS):
-            c0, c1 = c * BATCH // E2E_CHUNKS, (c + 1) * BATCH // E2E_CHUNKS
+            c0, c1 = cb[c], cb[c + 1]
             E.maplookup_(strategy, out_dev.cols(c0, c1), tables, [i.cols(c0, c1) for i in Is_buf[slot]])
             done = main.record_event()
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
                 out_dev.cols(c0, c1).download(out_pinned[:, c0:c1])   # D2H: the step's result, chunk c
-        upload_indices(1 - slot)                          # next step's indices, beside this step's D2H
-        # H2D: the upstream cotangent, once the host has the whole feature matrix; group g's rows
+                on_host = d2h_stream.record_event()
+            if c < E2E_DENSE:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(on_host)       # these samples' results are on the host
+                    delta_dev.cols(c0, c1).upload(delta_pinned[:, c0:c1])
+        if not DUPLEX:
+            upload_indices(1 - slot)                      # next step's indices, beside this step's D2H
+        # H2D: the rest of the upstream cotangent, once the host has the whole feature matrix; group g's rows
         # (the first slice also carries the PREPEND rows of the dense part: the whole matrix is copied)
         landed = []
+        t0 = cb[E2E_DENSE]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_stream(d2h_stream)
             for a, b in groups:
                 r0, r1 = (0 if a == 0 else PREPEND + a * DIM), PREPEND + b * DIM
-                delta_dev.rows(r0, r1).upload(delta_pinned[r0:r1])
+                delta_dev.rows(r0, r1).cols(t0, BATCH).upload(delta_pinned[r0:r1, t0:])
                 landed.append(copy_stream.record_event())
         slicer = E.Slicer(PREPEND + 1, 1, delta_dev)
         grads = [E.SparseEmbeddingUpdate(S, slicer(DIM), i) for i in Is_buf[slot]]
@@ -425,9 +443,13 @@ def run_ours(args):
         "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
                 "d2h_bytes_per_step": int(out_pinned.nbytes),
-                "pipeline": "indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent in %d "
-                            "table-group row slices (2-D H2D), each group's update! as its slice lands"
-                            % (E2E_CHUNKS, len(groups))},
+                "pipeline": ("indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent: the first %d "
+                             "column chunks each right behind its own result chunk (PCIe full duplex, per-sample dependency), the "
+                             "remaining columns in %d table-group row slices (2-D H2D), each group's update! as its slice lands"
+                             % (E2E_CHUNKS, E2E_DENSE, len(groups))) if DUPLEX else
+                            ("indices double-buffered; forward in %d column chunks with overlapped D2H; whole result on the host, then "
+                             "the cotangent in %d table-group row slices (2-D H2D), each group's update! as its slice lands"
+                             % (E2E_CHUNKS, len(groups)))},
         "gpu_launches": gpu_launches,
         "launches_per_step": launches,
         "clocks": clocks.result,
@@ -494,7 +516,8 @@ def run_sharded(args, rank, world, local):
     plan = ShardPlan([DIM] * (NT * world), world, rank, PREPEND, BATCH)
     fused = not args.nccl_a2a
     G = max(1, int(os.environ.get("ETB_TABLE_GROUPS", "1"))) if fused else 1   # measured on 8 GPUs: 1 group 3.64 ms, 2 groups 3.67, 4 groups 4.47
-    ens = ShardedEnsemble(tables, plan, fused=fused, table_groups=G, peer_barrier=not args.nccl_barrier)
+    ens = ShardedEnsemble(tables, plan, fused=fused, table_groups=G, peer_barrier=not args.nccl_barrier,
+                          copy_engine=args.exchange == "copy")
     G = ens.n_groups
     I_host = make_indices(rng, args.dist, NT, NROWS, BAG, BATCH)
     idx_pinned = E.pinned_empty((BAG, BATCH, NT), np.int64)
@@ -562,8 +585,12 @@ def run_sharded(args, rank, world, local):
     # step, pipelined like the N = 1 path: indices double-buffered (step k+1's upload beside step k's download), the
     # forward in column chunks whose D2H overlaps the next chunk's lookup, the cotangent in table-group row slices
     # (one strided copy per owner and group), each group's exchange + update! as its slice has landed.
+    # With ETB_E2E_DUPLEX (default) the cotangent of the first E2E_DENSE column chunks follows each chunk's own result
+    # (per-sample dependency, PCIe full duplex) exactly as at N = 1.
     copy_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
-    E2E_CHUNKS = 4 if fused else 1
+    DUPLEX = fused and os.environ.get("ETB_E2E_DUPLEX", "1") != "0"
+    E2E_CHUNKS = max(1, int(os.environ.get("ETB_E2E_CHUNKS", "8" if DUPLEX else "4"))) if fused else 1
+    E2E_DENSE = min(E2E_CHUNKS - 1, max(0, int(os.environ.get("ETB_E2E_DENSE", str(E2E_CHUNKS // 2))))) if DUPLEX else 0
     I_buf = [I_dev, E.DeviceArray.empty((BAG, BATCH, NT), np.int64)]
     idx_ready, buf_free, e2e_state = [None, None], [None, None], {"k": 0}
     cb = [round(c * plan.my_cols / E2E_CHUNKS) for c in range(E2E_CHUNKS + 1)]
@@ -590,23 +617,32 @@ def run_sharded(args, rank, world, local):
         main = torch.cuda.current_stream()
         main.wait_event(idx_ready[slot])
         idx_ready[slot] = None
+        if DUPLEX:
+            upload_indices(1 - slot)                       # next step's indices: first in the H2D queue
         for c in range(E2E_CHUNKS):
             ens.forward(I_buf[slot], cols=(cb[c], cb[c + 1]), prefetch_index=(c == 0))
             done = main.record_event()
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
                 ens.out.cols(cb[c], cb[c + 1]).download(out_pinned[:, cb[c]:cb[c + 1]])
-        upload_indices(1 - slot)
+                on_host = d2h_stream.record_event()
+            if c < E2E_DENSE and cb[c + 1] > cb[c]:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(on_host)        # these samples' results are on the host
+                    delta_dev.cols(cb[c], cb[c + 1]).upload(delta_pinned[:, cb[c]:cb[c + 1]])
+        if not DUPLEX:
+            upload_indices(1 - slot)
         landed = []
+        t0 = cb[E2E_DENSE]
         with torch.cuda.stream(copy_stream):
-            copy_stream.wait_stream(d2h_stream)            # the host has the whole result before the cotangent exists
+            copy_stream.wait_stream(d2h_stream)            # the host has the whole result before the rest of the cotangent exists
             for g in range(G):
                 for o in range(world):
                     r0 = plan.row_off[o] + ens.group_rows[o][g][0]
                     r1 = r0 + ens.group_rows[o][g][1]
                     if g == 0 and o == 0:
                         r0 = 0                             # the dense part's rows travel too: the whole matrix is copied
-                    delta_dev.rows(r0, r1).upload(delta_pinned[r0:r1])
+                    delta_dev.rows(r0, r1).cols(t0, plan.my_cols).upload(delta_pinned[r0:r1, t0:])
                 landed.append(copy_stream.record_event())
         ens.update_launches = 0
         for g in range(G):
@@ -676,15 +712,17 @@ def run_sharded(args, rank, world, local):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": common_config(world, args.dist),
             "exchange": ("NCCL all-to-all + pack/unpack kernels" if args.nccl_a2a else
-                         "fused: lookup / scatter kernels store into peer HBM over NVLink (CUDA IPC); " +
+                         ("fused: lookup / scatter kernels store into peer HBM over NVLink (CUDA IPC); " if not ens.copy_engine else
+                          "fused: kernels write local staging blocks, copy engines push them into peer HBM over NVLink (CUDA IPC); ") +
                          ("peer-memory flag barrier" if ens.peer_barrier else "NCCL all-reduce barrier") +
                          f"; backward exchange + update! pipelined over {G} table groups"),
             "self_check": check, "numa": numa,
             "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
                     "d2h_bytes_per_step": int(out_pinned.nbytes),
-                    "pipeline": ("indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent in %d "
-                                 "table-group row slices, each group's exchange + update! as its slice lands" % (E2E_CHUNKS, G))
+                    "pipeline": ("indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent: the first %d column "
+                                 "chunks each right behind its own result chunk (full duplex), the rest in %d table-group row slices, each "
+                                 "group's exchange + update! as its slice lands" % (E2E_CHUNKS, E2E_DENSE, G))
                                 if fused else "plain chain"},
             "gpu_launches": launches[0] * K, "clocks": clocks.result,
             "roofline": {"bound": "hbm", "kernel": "pooled_kernel+a2a (fwd phase, max over ranks)",
@@ -726,6 +764,9 @@ def main():
     ap.add_argument("--no-overlap", action="store_true", help="run index! after the forward instead of beside it")
     ap.add_argument("--nccl-a2a", action="store_true",
                     help="N>1: exchange with NCCL all-to-all + pack/unpack instead of fused NVLink peer stores")
+    ap.add_argument("--exchange", default=os.environ.get("ETB_EXCHANGE", "store"), choices=["store", "copy"],
+                    help="N>1, fused exchange: 'store' = the lookup / scatter kernels store into peer HBM; 'copy' = they write "
+                         "local staging blocks that the copy engines push over NVLink beside the next lookup")
     ap.add_argument("--nccl-barrier", action="store_true",
                     help="N>1, fused exchange: a one-element NCCL all-reduce as barrier instead of the peer-memory flags")
     ap.add_argument("--no-self-check", action="store_true", help="N>1: skip the sharded-vs-single-GPU check before timing")

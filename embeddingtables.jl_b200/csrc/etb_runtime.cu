@@ -157,6 +157,16 @@ int32_t etb_memcpy2d_d2h(void* dst_host, size_t dst_pitch, const void* src, size
     return ETB_OK;
 }
 
+int32_t etb_memcpy2d_d2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                         size_t height, void* stream) {
+    ETB_API_RANGE();
+    if (width_bytes == 0 || height == 0) return ETB_OK;
+    ETB_REQUIRE(dst && src, "etb_memcpy2d_d2d: null pointer");
+    ETB_REQUIRE(dst_pitch >= width_bytes && src_pitch >= width_bytes, "etb_memcpy2d_d2d: pitch smaller than the run");
+    ETB_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, cudaMemcpyDefault, (cudaStream_t)stream));
+    return ETB_OK;
+}
+
 int32_t etb_memset(void* dst, int32_t byte, size_t bytes, void* stream) {
     if (bytes == 0) return ETB_OK;
     ETB_REQUIRE(dst, "etb_memset: null pointer");

@@ -60,6 +60,7 @@ _SIGS = {
     "etb_memcpy_d2d": ([C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p], C.c_int32),
     "etb_memcpy2d_h2d": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p], C.c_int32),
     "etb_memcpy2d_d2h": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p], C.c_int32),
+    "etb_memcpy2d_d2d": ([C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p], C.c_int32),
     "etb_memset": ([C.c_void_p, C.c_int32, C.c_size_t, C.c_void_p], C.c_int32),
     "etb_stream_create": ([C.POINTER(C.c_void_p)], C.c_int32),
     "etb_stream_sync": ([C.c_void_p], C.c_int32),

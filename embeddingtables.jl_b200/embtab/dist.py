@@ -112,7 +112,7 @@ class ShardedEnsemble:
     """
 
     def __init__(self, tables_local, plan: ShardPlan, group=None, fused: bool = False, table_groups: int = 1,
-                 peer_barrier: bool = True):
+                 peer_barrier: bool = True, copy_engine: bool = False):
         """fused=False: NCCL all-to-all + pack/unpack kernels.  fused=True: the lookup kernel stores
         straight into the peers' feature matrices and the backward scatter straight into the owners'
         cotangent buffers over NVLink (CUDA-IPC mapped peer memory); ranks meet at a hand-written
@@ -121,6 +121,9 @@ class ShardedEnsemble:
         table group by table group and every owner updates group g while group g+1 is on the wire."""
         self.tables, self.plan, self.group, self.fused = list(tables_local), plan, group, bool(fused)
         self.peer_barrier = bool(peer_barrier) and self.fused
+        # copy_engine (fused only): the kernels write LOCAL staging blocks and the GPU's copy engines push them into
+        # the peers' buffers over NVLink (etb_memcpy2d_d2d) while the SMs look the next peer's columns up
+        self.copy_engine = bool(copy_engine) and self.fused
         assert len(self.tables) == len(plan.my_tables)
         if not self.tables:
             raise ValueError("every rank must own at least one table (fewer tables than ranks)")
@@ -214,6 +217,7 @@ class ShardedEnsemble:
             offs = (C.c_int64 * p.world)(*[p.row_off[q] + self.group_rows[q][g][0] for q in self._order])
             self._gscatter.append((ptrs, lds, rows, offs))
         self._upd_stream = torch.cuda.Stream()
+        self._copy_streams = [torch.cuda.Stream() for _ in range(2)]
         dist.barrier(group=self.group)
 
     def _barrier(self):
@@ -235,6 +239,58 @@ class ShardedEnsemble:
             for ptr in self._raw:
                 _lib.lib().etb_free(ptr)
             self._imported, self._raw, self.fused = [], [], False
+
+    def _forward_copy(self, Is):
+        """forward with the copy engines: one lookup launch per peer (all my tables, that peer's columns) into the local
+        send layout; as soon as a launch is done its block travels to the peer as ONE strided device-to-device copy,
+        beside the next peer's lookup.  My own columns come last and go straight into my feature matrix."""
+        p, lib, es = self.plan, _lib.lib(), np.dtype(self.dtype).itemsize
+        main = torch.cuda.current_stream()
+        send = DeviceArray(self.send.buf, (p.my_rows, p.batch_global), 0, p.my_rows, self.dtype)
+        self.launches = 0
+        order = self._order[:-1] + [p.rank] if self._order[-1] == p.rank else self._order
+        for k, q in enumerate(order):
+            if p.cols[q] == 0:
+                continue
+            items, off = [], 0
+            for t, i in zip(self.tables, Is):
+                f = featuresize(t)
+                if q == p.rank:
+                    dst = self.out.rows(p.row_off[p.rank] + off, p.row_off[p.rank] + off + f)
+                else:
+                    dst = send.rows(off, off + f).cols(p.clo[q], p.chi[q])
+                items.append(_item(t, i.cols(p.clo[q], p.chi[q]), dst))
+                off += f
+            _run(items)
+            self.launches += lib.etb_last_launch_count()
+            if q != p.rank:
+                cs = self._copy_streams[k % len(self._copy_streams)]
+                cs.wait_event(main.record_event())
+                _lib.check(lib.etb_memcpy2d_d2d(self._peer_out[q] + p.row_off[p.rank] * es, p.total_rows * es,
+                                                send.ptr + p.clo[q] * p.my_rows * es, p.my_rows * es, p.my_rows * es, p.cols[q],
+                                                C.c_void_p(cs.cuda_stream)))
+        for cs in self._copy_streams:
+            main.wait_stream(cs)
+        self._barrier()
+        return self.out
+
+    def _backward_copy(self, delta: DeviceArray):
+        """reverse exchange with the copy engines: the row block of every owner goes into that owner's cotangent
+        buffer as one strided copy; no SM is involved"""
+        p, lib, es = self.plan, _lib.lib(), np.dtype(self.dtype).itemsize
+        main = torch.cuda.current_stream()
+        ev = main.record_event()
+        for k, q in enumerate(self._order):
+            if p.rows[q] == 0 or p.my_cols == 0:
+                continue
+            cs = self._copy_streams[k % len(self._copy_streams)]
+            cs.wait_event(ev)
+            _lib.check(lib.etb_memcpy2d_d2d(self._peer_dglob[q] + p.clo[p.rank] * p.rows[q] * es, p.rows[q] * es,
+                                            delta.ptr + p.row_off[q] * es, delta.ld * es, p.rows[q] * es, p.my_cols,
+                                            C.c_void_p(cs.cuda_stream)))
+        for cs in self._copy_streams:
+            main.wait_stream(cs)
+        self._barrier()
 
     def _forward_fused(self, Is, cols=None):
         """cols = (c0, c1): only local columns c0..c1 of every rank's slice (the e2e path looks the batch up in column
@@ -308,6 +364,8 @@ class ShardedEnsemble:
                 self.index_launches += _lib.lib().etb_last_launch_count()
         if self.fused:
             assert out is None, "fused mode writes into the peer-mapped self.out"
+            if self.copy_engine and cols is None:
+                return self._forward_copy(Is)
             return self._forward_fused(Is, cols)
         assert cols is None
         out = self.out if out is None else out
@@ -334,7 +392,10 @@ class ShardedEnsemble:
     def backward(self, delta: DeviceArray):
         p = self.plan
         if self.fused:
-            self._backward_fused(delta)
+            if self.copy_engine:
+                self._backward_copy(delta)
+            else:
+                self._backward_fused(delta)
             return self._grads()
         n_send, n_recv = (p.total_rows - p.prependrows) * p.my_cols, p.my_rows * p.batch_global
         # pack my cotangent's row blocks by owner (reuses the forward receive buffer)

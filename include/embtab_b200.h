@@ -184,6 +184,10 @@ int32_t etb_memcpy2d_h2d(void* dst, size_t dst_pitch, const void* src_host, size
                          size_t height, void* stream);
 int32_t etb_memcpy2d_d2h(void* dst_host, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
                          size_t height, void* stream);
+/* device-to-device, also between a local buffer and a peer buffer mapped with etb_ipc_import: the copy engines move
+ * row blocks over NVLink while the SMs keep computing (the multi-GPU exchange of embtab/dist.py, exchange="copy") */
+int32_t etb_memcpy2d_d2d(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                         size_t height, void* stream);
 int32_t etb_memset(void* dst, int32_t byte, size_t bytes, void* stream);
 int32_t etb_stream_create(void** stream_host);
 int32_t etb_stream_sync(void* stream);

@@ -50,8 +50,11 @@ for t in range(len(base)):
 plan = ShardPlan(dims, world, rank, prepend, batch)
 mine = list(plan.my_tables)
 # NCCL all-to-all + pack/unpack; NVLink peer stores + NCCL barrier; peer stores + flag barrier + pipelined backward
-for fused, groups, peer_barrier in ((False, 1, False), (True, 1, False), (True, 3, True)):
-    ens = ShardedEnsemble([make_table(t) for t in mine], plan, fused=fused, table_groups=groups, peer_barrier=peer_barrier)
+# ...; the same with the copy engines carrying the blocks
+for fused, groups, peer_barrier, copy_engine in ((False, 1, False, False), (True, 1, False, False), (True, 3, True, False),
+                                                 (True, 1, True, True)):
+    ens = ShardedEnsemble([make_table(t) for t in mine], plan, fused=fused, table_groups=groups, peer_barrier=peer_barrier,
+                          copy_engine=copy_engine)
     ens.out.fill(-5.0)
     torch.cuda.synchronize()
     dist.barrier()
@@ -59,7 +62,7 @@ for fused, groups, peer_barrier in ((False, 1, False), (True, 1, False), (True, 
         out = ens.forward([I[t] for t in mine])
         got = out.numpy()
         want = orc_out[:, plan.clo[rank]:plan.chi[rank]]
-        assert np.array_equal(got[prepend:], want[prepend:]), f"sharded forward differs from the oracle (fused={fused})"
+        assert np.array_equal(got[prepend:], want[prepend:]), f"sharded forward differs from the oracle (fused={fused}, copy_engine={copy_engine})"
         assert np.all(got[:prepend] == -5.0), "prepend rows were touched"
         d_local = E.DeviceArray.from_numpy(delta[:, plan.clo[rank]:plan.chi[rank]])
         if rep == 0:
@@ -86,5 +89,5 @@ for wire in (None, np.int32):
 torch.cuda.synchronize()
 dist.barrier()
 if rank == 0:
-    print("dist check ok", world, "(sharded == single GPU == oracle, bit for bit: NCCL, fused + NCCL barrier, fused + peer-flag barrier + grouped backward)")
+    print("dist check ok", world, "(sharded == single GPU == oracle, bit for bit: NCCL, fused + NCCL barrier, fused + peer-flag barrier + grouped backward, copy engines)")
 dist.destroy_process_group()
