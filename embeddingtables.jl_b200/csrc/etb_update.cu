@@ -66,7 +66,7 @@ struct UpdParams {
     double eta;
     int32_t row_bits;
     int32_t slot0, nslots;  // this launch handles slots [slot0, slot0 + nslots)
-    int32_t G, nvec;
+    int32_t G, nvec, vb;
     int32_t fma, split_long;
     int32_t strict_long;  // strict order and the rows fit one pass: buckets of > kLongThreshold members go to long_strict_kernel
     int32_t num_splits, this_split;  // IndexerView, reference src/utils.jl:325-333
@@ -208,6 +208,13 @@ __device__ __noinline__ void register_strict_long_bucket(LongCounters* counters,
     longs[atomicAdd(&counters->n_long, 1u)] = LongRec{bucket, 0u, 0u, 0u};
 }
 
+// ... and of long_strict_sliced_kernel: the record carries everything a job needs (start, members, key), so that a job
+// starts after ONE dependent load instead of three
+__device__ __noinline__ void register_sliced_long_bucket(LongCounters* counters, LongRec* longs, uint32_t start, int cnt,
+                                                         uint64_t key) {
+    longs[atomicAdd(&counters->n_long, 1u)] = LongRec{start, (uint32_t)cnt, (uint32_t)key, (uint32_t)(key >> 32)};
+}
+
 __device__ __noinline__ void register_long_bucket(LongCounters* counters, LongRec* longs, ChunkRec* chunks,
                                                   uint32_t bucket, int cnt) {
     const uint32_t nch = (uint32_t)((cnt + kLongChunk - 1) / kLongChunk);
@@ -275,6 +282,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
         int cnt = mine ? (int)(stop - start) : 0;
         if (cnt > kShortMax) {
             if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            else if (P.strict_long == 2 && cnt > kLongThreshold) register_sliced_long_bucket(P.counters, P.longs, (uint32_t)start, cnt, key);
             else if (P.strict_long && cnt > kLongThreshold) register_strict_long_bucket(P.counters, P.longs, (uint32_t)s);
             else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
@@ -407,6 +415,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
         int cnt = mine ? (int)(stop - (int64_t)raw.x) : 0;
         if (cnt > kShortMax) {
             if (P.split_long && cnt > kLongThreshold) register_long_bucket(P.counters, P.longs, P.chunks, (uint32_t)s, cnt);
+            else if (P.strict_long == 2 && cnt > kLongThreshold) register_sliced_long_bucket(P.counters, P.longs, raw.x, cnt, key);
             else if (P.strict_long && cnt > kLongThreshold) register_strict_long_bucket(P.counters, P.longs, (uint32_t)s);
             else P.chunks[atomicAdd(&P.counters->n_chunks, 1u)] = ChunkRec{kMediumTask, (uint32_t)s};
             cnt = 0;
@@ -859,13 +868,32 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
     }
 }
 
-// The same job with Blackwell's bulk-copy engine (rows of 16-byte vectors): warp 1 asks the TMA unit for one member
-// row per lane -- cp.async.bulk, 32 rows = one stage, completion counted in bytes on the stage's mbarrier -- and
-// warp 0 adds the rows of a stage once its barrier has flipped, then hands the stage back through a second
-// mbarrier.  No thread copies data or computes piece addresses; 6 stages of 32 rows (up to 80 KB) are in flight.
-// MEASURED SLOWER than the cp.async kernel above (C3: 2.08 vs 1.01 ms): a bulk request per 512-byte row pays the
-// copy engine's per-request cost 45 000 times.  Kept behind ETB_STRICT_BULK=1 as the evidence.
-constexpr int kBulkStages = 6, kBulkRows = 32, kBulkThreads = 64;
+// The same job SLICED BY FEATURES (SGD; the default).  The strict order binds the members of ONE feature element into a
+// chain; different elements are independent.  One CTA streaming whole 512-byte rows is bound by what a single SM pulls
+// from L2 / HBM and by four adds per member in its one adding warp (measured: 15 ns per member), far from the chain's
+// own cost (one dependent add per member).  So a long bucket becomes ceil(dim / 32) jobs, one per slice of 32 consecutive
+// elements; the slices of a bucket run on different SMs at the same time.  In a job
+//   * warps 1..7 stream that slice of every member row into shared memory (cp.async, VB-byte pieces, stages of up to 128
+//     members) and warp 0 adds: lane l owns element l of the slice -- one shared-memory load and ONE dependent add per
+//     member, the loads of the next members in flight beside the adds.
+//   * The members' delta columns (the map) travel like the rows: batch b's copies also fetch the map of batch b + S into
+//     a ring of 2 S slots, so it has landed when the stage is handed back for batch b + S.  (Prefetched into registers,
+//     every batch waited for the NEWEST map load -- the loads share scoreboards -- i.e. one DRAM round trip per batch.)
+//   * Stages are handed over through mbarriers: s_full[st] gets one arrival per producer thread, delivered by the copy
+//     unit when that thread's pieces have landed (cp.async.mbarrier.arrive.noinc: nobody waits for a landing but the
+//     adding warp); s_empty[st] one arrival from the adding warp.  The ring runs on across the CTA's jobs: the
+//     producers are already loading the next job's first batches while warp 0 finishes the current one.
+// Any row length (slices are independent), any alignment class, any floating-point element type.
+#ifndef ETB_SLICE_STAGES
+#define ETB_SLICE_STAGES 4
+#endif
+#ifndef ETB_SLICE_CTAS
+#define ETB_SLICE_CTAS 3
+#endif
+#ifndef ETB_SLICE_U
+#define ETB_SLICE_U 16
+#endif
+constexpr int kSliceElems = 32, kSliceStages = ETB_SLICE_STAGES, kSliceStageBytes = 16 * 1024, kSliceMaxRows = 128, kSlicePieces = 5;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -884,6 +912,163 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
                      : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
     } while (!ok);
 }
+// the mbarrier gets one arrival from this thread once all cp.async it has issued so far have landed (no waiting here)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void lds_elem(T* out, const char* p) {  // volatile: the adding warp wants them issued in a batch
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    if constexpr (sizeof(T) == 8) {
+        unsigned long long v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a));
+        *(unsigned long long*)out = v;
+    } else if constexpr (sizeof(T) == 4) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        *(uint32_t*)out = v;
+    } else {
+        unsigned short v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+        *(unsigned short*)out = v;
+    }
+}
+
+template <typename T, int VB>
+__global__ void __launch_bounds__(kUThreads)
+long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
+    using A = acc_t<T>;
+    extern __shared__ __align__(16) char s_rows[];  // [S][R][SB]
+    constexpr int kProducers = kUThreads - 32;
+    constexpr int SB = kSliceElems * (int)sizeof(T);  // bytes of a full slice (64 / 128 / 256): the row pitch of a stage
+    constexpr int U = ETB_SLICE_U;
+    constexpr int S = kSliceStages;
+    __shared__ __align__(8) uint64_t s_full[S], s_empty[S];
+    __shared__ int32_t s_map[2 * S][kSliceMaxRows];
+    const int row_bytes = P.nvec * VB;
+    const int dim = row_bytes / (int)sizeof(T);
+    const int nsl = (dim + kSliceElems - 1) / kSliceElems;
+    const int lane = threadIdx.x & 31;
+    const bool consumer = threadIdx.x < 32;  // warp 0 adds, warps 1..7 load
+    const uint32_t n_jobs = P.counters->n_long * (uint32_t)nsl;
+    const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
+    const A eta = (A)P.eta;
+    if (threadIdx.x < S) {
+        mbar_init(&s_full[threadIdx.x], kProducers);
+        mbar_init(&s_empty[threadIdx.x], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // gb counts this CTA's batches over all its jobs: batch gb lives in stage gb % S and is that stage's (gb / S)-th use
+    // (= the barrier phase).  Both sides walk the same (job, batch) sequence, each at its own pace.
+    uint32_t gb = 0;
+    uint4 lr_next = make_uint4(0, 0, 0, 0);  // the next job's record is fetched while this job runs
+    if (blockIdx.x < n_jobs) lr_next = __ldg((const uint4*)(P.longs + blockIdx.x / (uint32_t)nsl));
+    for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const uint32_t j = job / (uint32_t)nsl;
+        const int sl = (int)(job - j * (uint32_t)nsl);
+        const int sbytes = min(SB, row_bytes - sl * SB);  // this slice's bytes of a row (a multiple of VB)
+        const int pps = sbytes / VB;                      // pieces per member row
+        const int R = min(min(kSliceMaxRows, kSliceStageBytes / SB), kSlicePieces * kProducers / pps);
+        const uint4 lr = lr_next;  // {start, members, key} (register_sliced_long_bucket)
+        if (job + gridDim.x < n_jobs) lr_next = __ldg((const uint4*)(P.longs + (job + gridDim.x) / (uint32_t)nsl));
+        const int64_t start = lr.x;
+        const int members = (int)lr.y;
+        const uint64_t key = ((uint64_t)lr.w << 32) | lr.z;
+        const int slot = (int)(key >> P.row_bits) - P.slot0;
+        const UpdDesc& d = P.item[slot];
+        const int nbatch = (members + R - 1) / R;
+        if (consumer) {
+            const bool on = sl * kSliceElems + lane < dim;
+            T* mine_row = nullptr;
+            T old = T();
+            if (on) {
+                mine_row = (T*)const_cast<char*>(row_ptr(d.table, (int64_t)(key & row_mask) + 1)) + sl * kSliceElems + lane;
+                old = *mine_row;
+            }
+            A acc = A(0);  // accum = zero, then += members in order
+            for (int b = 0; b < nbatch; ++b, ++gb) {
+                const int st = (int)(gb % S);
+                mbar_wait(&s_full[st], (gb / S) & 1u);  // batch b has landed
+                const int rows = min(R, members - b * R);
+                const char* mine = s_rows + st * kSliceStageBytes + lane * (int)sizeof(T);
+                T va[U], vb2[U];
+                int r = 0;
+                if (rows >= U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) lds_elem<T>(&va[u], mine + u * SB);
+                }
+                // two groups of U per turn: the loads of one group are in flight beside the other group's chain of adds
+                for (; r + 3 * U <= rows; r += 2 * U) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) lds_elem<T>(&vb2[u], mine + (r + U + u) * SB);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(va[u]);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) lds_elem<T>(&va[u], mine + (r + 2 * U + u) * SB);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(vb2[u]);
+                }
+                if (rows >= U) {  // va holds rows r .. r + U - 1
+#pragma unroll
+                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(va[u]);
+                    r += U;
+                }
+                for (; r < rows; ++r) {
+                    T v;
+                    lds_elem<T>(&v, mine + r * SB);
+                    acc = acc + to_acc<T>(v);
+                }
+                __syncwarp();  // the stage may be overwritten (by this CTA's batch gb + S, if there is one)
+                if (lane == 0) mbar_arrive(&s_empty[st]);
+            }
+            if (on) *mine_row = sgd_apply<T>(old, acc, eta, d.table.pad != 0);
+        } else {
+            // a producer's pieces of a batch: piece pc = (tid - 32) + k * 224 is piece pc % pps of the batch's row pc / pps
+            int pr[kSlicePieces], poff[kSlicePieces], pvb[kSlicePieces];
+            const int t = (int)threadIdx.x - 32;
+#pragma unroll
+            for (int k = 0; k < kSlicePieces; ++k) {
+                const int pc = t + k * kProducers;
+                pr[k] = pc / pps;  // rows >= R never exist
+                pvb[k] = (pc - pr[k] * pps) * VB;
+                poff[k] = pr[k] * SB + pvb[k];
+            }
+            const int32_t* bmap = P.map + start;
+            const char* dbase = d.delta + (size_t)sl * SB;
+            const int64_t ldb = d.ld_delta_bytes;
+            // the map of the job's first S batches: one round trip per job (their slots were last read 2 S batches ago)
+            for (int i = t; i < min(members, S * R); i += kProducers) s_map[(gb + i / R) % (2 * S)][i % R] = __ldg(bmap + i);
+            asm volatile("bar.sync 1, %0;" ::"n"(kProducers) : "memory");  // the producer warps only
+            for (int b = 0; b < nbatch; ++b, ++gb) {
+                const int st = (int)(gb % S);
+                if (gb >= S) mbar_wait(&s_empty[st], (gb / S - 1) & 1u);  // the stage's previous batch has been added
+                const int rows = min(R, members - b * R);
+                const int32_t* m = s_map[gb % (2 * S)];  // filled above or with this CTA's batch gb - S
+                int32_t c[kSlicePieces];
+#pragma unroll
+                for (int k = 0; k < kSlicePieces; ++k) c[k] = pr[k] < rows ? m[pr[k]] : 0;
+                char* stage = s_rows + st * kSliceStageBytes;
+#pragma unroll
+                for (int k = 0; k < kSlicePieces; ++k)
+                    if (pr[k] < rows) cp_async<VB>(stage + poff[k], dbase + (int64_t)c[k] * ldb + pvb[k]);
+                if (t < R && (b + S) * R + t < members)  // the map of batch b + S
+                    cp_async<4>(&s_map[(gb + S) % (2 * S)][t], bmap + (b + S) * R + t);
+                cp_async_arrive(&s_full[st]);  // every producer thread, with or without pieces in this batch
+            }
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// The same job with Blackwell's bulk-copy engine (rows of 16-byte vectors): warp 1 asks the TMA unit for one member
+// row per lane -- cp.async.bulk, 32 rows = one stage, completion counted in bytes on the stage's mbarrier -- and
+// warp 0 adds the rows of a stage once its barrier has flipped, then hands the stage back through a second
+// mbarrier.  No thread copies data or computes piece addresses; 6 stages of 32 rows (up to 80 KB) are in flight.
+// MEASURED SLOWER than the cp.async kernel above (C3: 2.08 vs 1.01 ms): a bulk request per 512-byte row pays the
+// copy engine's per-request cost 45 000 times.  Kept behind ETB_STRICT_BULK=1 as the evidence.
+constexpr int kBulkStages = 6, kBulkRows = 32, kBulkThreads = 64;
+
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -1072,6 +1257,12 @@ static UpdClass classify_update(const etb_update_item& it) {
 
 enum { kKernelMain = 0, kKernelTasks = 1, kKernelCombine = 2, kKernelStrictLong = 3 };
 
+// ETB_STRICT_SLICED=0: round 2's one-CTA-per-bucket kernel for the long buckets of the strict order (kept for comparison)
+static bool strict_sliced() {
+    static const bool on = [] { const char* e = getenv("ETB_STRICT_SLICED"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <typename T, int VB, int VPL, int OPT>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
     if (which == kKernelMain) sgd_update_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
@@ -1087,6 +1278,14 @@ static void launch_update_one(int which, int grid, cudaStream_t s, const UpdPara
             }
             long_strict_bulk_kernel<T, VPL, OPT><<<grid, kBulkThreads, smem, s>>>(P);
         }
+    } else if (which == kKernelStrictLong && P.strict_long == 2) {  // the feature-sliced kernel (SGD)
+        constexpr int kSmem = kSliceStages * kSliceStageBytes;  // 64 KB of dynamic shared memory: three CTAs per SM
+        static thread_local bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(long_strict_sliced_kernel<T, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            configured = true;
+        }
+        long_strict_sliced_kernel<T, VB><<<grid, kUThreads, kSmem, s>>>(P);
     } else if (which == kKernelStrictLong) {
         constexpr int kSmem = kStrictStages * kStrictStageBytes;  // 96 KB of dynamic shared memory: opt in once
         static thread_local bool configured = false;
@@ -1137,13 +1336,18 @@ static void launch_update_opt(int which, const UpdClass& c, int grid, cudaStream
     if (which == kKernelMain && ETB_UPDATE_USE_EXACT) {
         bool done;
         switch (c.elt) {
-            case ETB_F32: done = launch_update_exact<float, OPT>(c, grid, s, P); break;
+#ifndef ETB_DEV_F32_ONLY
             case ETB_F16: done = launch_update_exact<__half, OPT>(c, grid, s, P); break;
             case ETB_BF16: done = launch_update_exact<__nv_bfloat16, OPT>(c, grid, s, P); break;
-            default: done = launch_update_exact<double, OPT>(c, grid, s, P); break;
+            case ETB_F64: done = launch_update_exact<double, OPT>(c, grid, s, P); break;
+#endif
+            default: done = launch_update_exact<float, OPT>(c, grid, s, P); break;
         }
         if (done) return;
     }
+#ifdef ETB_DEV_F32_ONLY  // experiment builds (tools/): Float32 tables only, a quarter of the compile time
+    return launch_update_vb<float, OPT>(which, c, grid, s, P);
+#endif
     switch (c.elt) {
         case ETB_F32: launch_update_vb<float, OPT>(which, c, grid, s, P); break;
         case ETB_F16: launch_update_vb<__half, OPT>(which, c, grid, s, P); break;
@@ -1225,8 +1429,11 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         P.nslots = n;
         P.G = c.G;
         P.nvec = c.nvec;
+        P.vb = c.vb;
         // strict order: long buckets whose rows fit one pass (and one 32 KB stage) are streamed by long_strict_kernel
-        P.strict_long = (!P.split_long && c.nvec <= c.G * c.vpl && c.nvec * c.vb <= kStrictStageBytes) ? 1 : 0;
+        // (the feature-sliced SGD kernel takes rows of any length)
+        const bool sliced = opt == kOptSgd && strict_sliced();
+        P.strict_long = P.split_long ? 0 : (sliced ? 2 : ((c.nvec <= c.G * c.vpl && c.nvec * c.vb <= kStrictStageBytes) ? 1 : 0));
         ETB_CUDA(cudaMemsetAsync(P.counters, 0, sizeof(LongCounters), stream));
         const int64_t buckets_per_block = (kUThreads / 32) * 32 * ETB_UPDATE_RPL;  // one tile per warp
         const int grid = (int)((view->n_total + buckets_per_block - 1) / buckets_per_block);
@@ -1241,7 +1448,8 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         }
         if (P.strict_long && view->n_total > kLongThreshold) {
             const int64_t max_long = view->n_total / kLongThreshold + 1;
-            const int gridS = (int)std::min<int64_t>(max_long, (int64_t)num_sms() * 2);  // one CTA per long bucket
+            const int64_t nsl = sliced ? ((int64_t)c.nvec * c.vb / (int64_t)elt_bytes(c.elt) + kSliceElems - 1) / kSliceElems : 1;
+            const int gridS = (int)std::min<int64_t>(max_long * nsl, (int64_t)num_sms() * (sliced ? ETB_SLICE_CTAS : 2));  // one CTA per job
             launch_update(opt, kKernelStrictLong, c, gridS, stream, P);
             ETB_LAUNCHED();
         }

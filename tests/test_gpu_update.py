@@ -253,7 +253,9 @@ def test_update_rejects_integer_tables(E):
         E.update_(E.Descent(0.1), t, g)
 
 
-@pytest.mark.parametrize("dim,dtype", [(128, np.float32), (16, np.float32), (40, np.float64), (520, np.float32)])
+@pytest.mark.parametrize("dim,dtype", [(128, np.float32), (16, np.float32), (40, np.float64), (520, np.float32),
+                                       # the feature-sliced strict kernel: partial last slice, 4-byte pieces, multi-pass rows
+                                       (80, np.float32), (5, np.float32), (33, np.float32), (1504, np.float32), (130, np.float64)])
 def test_split_long_zipf(E, O, dim, dtype, order):
     # Zipf(1.05)-like duplicates over several tables: many long buckets of different lengths,
     # through the ensemble path; several group widths / vector counts
