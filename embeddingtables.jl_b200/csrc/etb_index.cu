@@ -101,7 +101,10 @@ static cudaError_t ix_launch_pass(const IxParams& P, cudaStream_t s) {
     const int nb = 1 << P.width[P.pass];
     ix_hist_kernel<KeyT, SrcT, THREADS><<<P.ntiles, THREADS, 0, s>>>(P);
     ++launch_counter();
-    ix_scan_kernel<<<dim3((nb + 255) / 256, P.n_items), 256, 0, s>>>(P, THREADS * kIxItems);
+    if ((int64_t)nb * P.n_items < 8192)  // few (table, digit) pairs: a warp each
+        ix_scan_warp_kernel<<<dim3((nb + 7) / 8, P.n_items), 256, 0, s>>>(P, THREADS * kIxItems);
+    else
+        ix_scan_kernel<<<dim3((nb + 255) / 256, P.n_items), 256, 0, s>>>(P, THREADS * kIxItems);
     ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -871,11 +871,13 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
 // The same job SLICED BY FEATURES (SGD; the default).  The strict order binds the members of ONE feature element into a
 // chain; different elements are independent.  One CTA streaming whole 512-byte rows is bound by what a single SM pulls
 // from L2 / HBM and by four adds per member in its one adding warp (measured: 15 ns per member), far from the chain's
-// own cost (one dependent add per member).  So a long bucket becomes ceil(dim / 32) jobs, one per slice of 32 consecutive
-// elements; the slices of a bucket run on different SMs at the same time.  In a job
-//   * warps 1..7 stream that slice of every member row into shared memory (cp.async, VB-byte pieces, stages of up to 128
-//     members) and warp 0 adds: lane l owns element l of the slice -- one shared-memory load and ONE dependent add per
-//     member, the loads of the next members in flight beside the adds.
+// own cost (one dependent add per member: 4 cycles = 2 ns).  So a long bucket becomes ceil(dim / 16) jobs, one per
+// slice of 16 consecutive elements; the slices of a bucket run on different SMs at the same time.  In a job
+//   * warps 1..7 stream that slice of every member row into shared memory (cp.async, VB-byte pieces, 16 KB stages of
+//     up to 256 members) and warp 0 adds: lane l owns element l of the slice -- one shared-memory load and ONE dependent
+//     add per member, the loads of the next 16 members in flight beside the adds (tools/ubench_chain.cu: 4.8 cycles per
+//     member for that loop alone; in the kernel 6.2 + 300 per batch = 7.4 cycles per member, clock64-instrumented with
+//     -DETB_SLICE_PROFILE).
 //   * The members' delta columns (the map) travel like the rows: batch b's copies also fetch the map of batch b + S into
 //     a ring of 2 S slots, so it has landed when the stage is handed back for batch b + S.  (Prefetched into registers,
 //     every batch waited for the NEWEST map load -- the loads share scoreboards -- i.e. one DRAM round trip per batch.)
@@ -884,16 +886,24 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
 //     adding warp); s_empty[st] one arrival from the adding warp.  The ring runs on across the CTA's jobs: the
 //     producers are already loading the next job's first batches while warp 0 finishes the current one.
 // Any row length (slices are independent), any alignment class, any floating-point element type.
+// Measured (C3, hottest row 45 280 members): 0.80 ms -> 0.19 ms for the long buckets; a variant with the stage transposed
+// in quads of members (one 16-byte shared-memory load per 4 members, 4.3 cycles per member in the microbenchmark) was
+// built and was bound by its 4-byte cp.async producers instead (27 cycles per member): not kept.
 #ifndef ETB_SLICE_STAGES
 #define ETB_SLICE_STAGES 4
 #endif
 #ifndef ETB_SLICE_CTAS
-#define ETB_SLICE_CTAS 3
+#define ETB_SLICE_CTAS 4
 #endif
 #ifndef ETB_SLICE_U
 #define ETB_SLICE_U 16
 #endif
-constexpr int kSliceElems = 32, kSliceStages = ETB_SLICE_STAGES, kSliceStageBytes = 16 * 1024, kSliceMaxRows = 128, kSlicePieces = 5;
+#ifndef ETB_SLICE_ELEMS
+#define ETB_SLICE_ELEMS 16  /* 16 elements x 256 members per 16 KB stage: 7.4 cycles per member; 32 x 128: 8.6; 8 x 512: 7.2 */
+#endif
+constexpr int kSliceElems = ETB_SLICE_ELEMS, kSliceStages = ETB_SLICE_STAGES, kSliceStageBytes = 16 * 1024,
+              kSliceMaxRows = kSliceStageBytes / (kSliceElems * 4), kSlicePieces = 5;
+static_assert(kSliceElems == 8 || kSliceElems == 16 || kSliceElems == 32, "a slice is a fraction of a warp");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -979,7 +989,7 @@ long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
         const UpdDesc& d = P.item[slot];
         const int nbatch = (members + R - 1) / R;
         if (consumer) {
-            const bool on = sl * kSliceElems + lane < dim;
+            const bool on = lane < kSliceElems && sl * kSliceElems + lane < dim;
             T* mine_row = nullptr;
             T old = T();
             if (on) {
@@ -987,41 +997,82 @@ long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
                 old = *mine_row;
             }
             A acc = A(0);  // accum = zero, then += members in order
+#ifdef ETB_SLICE_PROFILE
+            long long prof_wait = 0, prof_add = 0;
+#endif
             for (int b = 0; b < nbatch; ++b, ++gb) {
                 const int st = (int)(gb % S);
+#ifdef ETB_SLICE_PROFILE
+                const long long tp0 = clock64();
+#endif
                 mbar_wait(&s_full[st], (gb / S) & 1u);  // batch b has landed
+#ifdef ETB_SLICE_PROFILE
+                const long long tp1 = clock64();
+                prof_wait += tp1 - tp0;
+#endif
                 const int rows = min(R, members - b * R);
-                const char* mine = s_rows + st * kSliceStageBytes + lane * (int)sizeof(T);
+                const char* mine = s_rows + st * kSliceStageBytes + min(lane, kSliceElems - 1) * (int)sizeof(T);
+                // Groups of U members, double buffered: the loads of one group are in flight beside the other group's
+                // chain of adds.  Every load of the batch is issued at least one group ahead of its add -- also the last
+                // full group and the partial one (a member-by-member tail pays the shared-memory latency per member:
+                // measured 9.2 cycles per member instead of 4.9, tools/ubench_chain.cu).
                 T va[U], vb2[U];
                 int r = 0;
-                if (rows >= U) {
+                const int left = rows % U;  // members of the partial group, loaded (predicated) beside the last full one
+                auto load_group = [&](T (&v)[U], int r0) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) lds_elem<T>(&va[u], mine + u * SB);
-                }
-                // two groups of U per turn: the loads of one group are in flight beside the other group's chain of adds
-                for (; r + 3 * U <= rows; r += 2 * U) {
+                    for (int u = 0; u < U; ++u) lds_elem<T>(&v[u], mine + (r0 + u) * SB);
+                };
+                auto load_partial = [&](T (&v)[U], int r0) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) lds_elem<T>(&vb2[u], mine + (r + U + u) * SB);
+                    for (int u = 0; u < U; ++u)
+                        if (u < left) lds_elem<T>(&v[u], mine + (r0 + u) * SB);
+                };
+                auto add_group = [&](const T (&v)[U]) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(va[u]);
+                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(v[u]);
+                };
+                auto add_partial = [&](const T (&v)[U]) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) lds_elem<T>(&va[u], mine + (r + 2 * U + u) * SB);
-#pragma unroll
-                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(vb2[u]);
-                }
-                if (rows >= U) {  // va holds rows r .. r + U - 1
-#pragma unroll
-                    for (int u = 0; u < U; ++u) acc = acc + to_acc<T>(va[u]);
-                    r += U;
-                }
-                for (; r < rows; ++r) {
-                    T v;
-                    lds_elem<T>(&v, mine + r * SB);
-                    acc = acc + to_acc<T>(v);
+                    for (int u = 0; u < U; ++u)
+                        if (u < left) acc = acc + to_acc<T>(v[u]);
+                };
+                if (rows < U) {
+                    load_partial(va, 0);
+                    add_partial(va);
+                } else {
+                    load_group(va, 0);
+                    for (;;) {  // va holds the group at r
+                        if (r + 2 * U > rows) {  // the last full group
+                            if (left) load_partial(vb2, r + U);
+                            add_group(va);
+                            if (left) add_partial(vb2);
+                            break;
+                        }
+                        load_group(vb2, r + U);
+                        add_group(va);
+                        r += U;  // vb2 holds the group at r
+                        if (r + 2 * U > rows) {
+                            if (left) load_partial(va, r + U);
+                            add_group(vb2);
+                            if (left) add_partial(va);
+                            break;
+                        }
+                        load_group(va, r + U);
+                        add_group(vb2);
+                        r += U;
+                    }
                 }
                 __syncwarp();  // the stage may be overwritten (by this CTA's batch gb + S, if there is one)
                 if (lane == 0) mbar_arrive(&s_empty[st]);
+#ifdef ETB_SLICE_PROFILE
+                prof_add += clock64() - tp1;
+#endif
             }
+#ifdef ETB_SLICE_PROFILE
+            if (lane == 0 && members > 20000)
+                printf("job %u slice %d members %d batches %d: wait %lld add %lld cycles\n", job, sl, members, nbatch, prof_wait, prof_add);
+#endif
             if (on) *mine_row = sgd_apply<T>(old, acc, eta, d.table.pad != 0);
         } else {
             // a producer's pieces of a batch: piece pc = (tid - 32) + k * 224 is piece pc % pps of the batch's row pc / pps
@@ -1052,8 +1103,8 @@ long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
 #pragma unroll
                 for (int k = 0; k < kSlicePieces; ++k)
                     if (pr[k] < rows) cp_async<VB>(stage + poff[k], dbase + (int64_t)c[k] * ldb + pvb[k]);
-                if (t < R && (b + S) * R + t < members)  // the map of batch b + S
-                    cp_async<4>(&s_map[(gb + S) % (2 * S)][t], bmap + (b + S) * R + t);
+                for (int i = t; i < R && (b + S) * R + i < members; i += kProducers)  // the map of batch b + S
+                    cp_async<4>(&s_map[(gb + S) % (2 * S)][i], bmap + (b + S) * R + i);
                 cp_async_arrive(&s_full[st]);  // every producer thread, with or without pieces in this batch
             }
         }
