@@ -533,10 +533,16 @@ def run_sharded(args, rank, world, local):
     opt = E.Descent(ETA)
     launches = [0]
 
+    # index! needs only the indices: it runs on a side stream beside the forward ("forward") or beside the backward
+    # exchange ("exchange": that phase is NVLink-bound and leaves HBM idle, while lookup and index! compete for it)
+    IDX_BESIDE = args.index_beside
+
     def step(events=None, pipelined=True):
-        ens.forward(I_dev)
+        ens.forward(I_dev, prefetch_index=IDX_BESIDE == "forward")
         n = ens.launches + (1 if ens.peer_barrier else 0)
         if events: events[1].record()
+        if IDX_BESIDE == "exchange":
+            ens.prefetch_index()
         if pipelined:      # backward exchange and update!, table group by table group
             ens.backward_update_(opt, delta_dev)
             n += ens.update_launches + ens.index_launches + 2 * G
@@ -715,7 +721,7 @@ def run_sharded(args, rank, world, local):
                          ("fused: lookup / scatter kernels store into peer HBM over NVLink (CUDA IPC); " if not ens.copy_engine else
                           "fused: kernels write local staging blocks, copy engines push them into peer HBM over NVLink (CUDA IPC); ") +
                          ("peer-memory flag barrier" if ens.peer_barrier else "NCCL all-reduce barrier") +
-                         f"; backward exchange + update! pipelined over {G} table groups"),
+                         f"; backward exchange + update! pipelined over {G} table groups; index! beside the {IDX_BESIDE}"),
             "self_check": check, "numa": numa,
             "e2e": {"value": lookups / (e2e_ms * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(idx_pinned.nbytes + delta_pinned.nbytes),
@@ -767,6 +773,8 @@ def main():
     ap.add_argument("--exchange", default=os.environ.get("ETB_EXCHANGE", "store"), choices=["store", "copy"],
                     help="N>1, fused exchange: 'store' = the lookup / scatter kernels store into peer HBM; 'copy' = they write "
                          "local staging blocks that the copy engines push over NVLink beside the next lookup")
+    ap.add_argument("--index-beside", default=os.environ.get("ETB_INDEX_BESIDE", "forward"), choices=["forward", "exchange"],
+                    help="N>1: run index! (side stream) beside the forward lookup or beside the backward exchange")
     ap.add_argument("--nccl-barrier", action="store_true",
                     help="N>1, fused exchange: a one-element NCCL all-reduce as barrier instead of the peer-memory flags")
     ap.add_argument("--no-self-check", action="store_true", help="N>1: skip the sharded-vs-single-GPU check before timing")

@@ -54,6 +54,37 @@ inline bool idx_elt_valid(int32_t e) { return e == ETB_I32 || e == ETB_I64; }
 
 int num_sms();  // multiprocessors of the current device (148 on B200), queried once per thread and device
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library starts with pdl_begin(): it lets the NEXT kernel of the stream be scheduled as soon as all
+// CTAs of this one are resident (its CTAs fill the SMs that this kernel's last wave leaves) and then waits until the
+// PREVIOUS kernel has completed and its writes are visible -- before the first global access.  Chains of small kernels
+// (index! is 9 to 11 launches) then pay the launch latency once instead of per kernel.  Launches go through launch_k(),
+// which sets the programmatic-stream-serialization attribute when ETB_PDL=1.  MEASURED AND LEFT OFF BY DEFAULT: eager
+// launches gain (C3 update! 144 -> 122 us at n = 65536), but the numbers that count are CUDA-graph replays, and there
+// the programmatic edges lose (C3 index! 67 -> 106 us, C1 49 -> 50 us, C2 unchanged).  Without the attribute the two
+// instructions of pdl_begin() do nothing.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_begin() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface in cudaGetLastError()
+}
+#endif
+
 inline int pow2ceil(int x) {
     int p = 1;
     while (p < x) p <<= 1;

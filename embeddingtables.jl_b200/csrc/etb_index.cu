@@ -99,12 +99,12 @@ int32_t make_layout(const etb_update_item* items, int32_t n_items, IndexLayout& 
 template <typename KeyT, typename SrcT, int RANK, int THREADS>
 static cudaError_t ix_launch_pass(const IxParams& P, cudaStream_t s) {
     const int nb = 1 << P.width[P.pass];
-    ix_hist_kernel<KeyT, SrcT, THREADS><<<P.ntiles, THREADS, 0, s>>>(P);
+    launch_k(ix_hist_kernel<KeyT, SrcT, THREADS>, P.ntiles, THREADS, 0, s, P);
     ++launch_counter();
     if ((int64_t)nb * P.n_items < 8192)  // few (table, digit) pairs: a warp each
-        ix_scan_warp_kernel<<<dim3((nb + 7) / 8, P.n_items), 256, 0, s>>>(P, THREADS * kIxItems);
+        launch_k(ix_scan_warp_kernel, dim3((nb + 7) / 8, P.n_items), 256, 0, s, P, THREADS * kIxItems);
     else
-        ix_scan_kernel<<<dim3((nb + 255) / 256, P.n_items), 256, 0, s>>>(P, THREADS * kIxItems);
+        launch_k(ix_scan_kernel, dim3((nb + 255) / 256, P.n_items), 256, 0, s, P, THREADS * kIxItems);
     ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -117,7 +117,7 @@ static cudaError_t ix_launch_pass(const IxParams& P, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    ix_scatter_kernel<KeyT, SrcT, RANK, THREADS><<<P.ntiles, THREADS, smem, s>>>(P);
+    launch_k(ix_scatter_kernel<KeyT, SrcT, RANK, THREADS>, P.ntiles, THREADS, smem, s, P);
     ++launch_counter();
     return cudaGetLastError();
 }
@@ -224,7 +224,7 @@ int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int3
             ETB_CUDA(cudaFuncSetAttribute(ix_small_kernel<uint32_t, SRC, RK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
             configured = smem;                                                                                             \
         }                                                                                                                  \
-        ix_small_kernel<uint32_t, SRC, RK><<<P.n_items, kIxThreads, smem, stream>>>(P, L.npasses);                         \
+        launch_k(ix_small_kernel<uint32_t, SRC, RK>, P.n_items, kIxThreads, smem, stream, P, L.npasses);                         \
     } while (0)
                 if (idx_elt == ETB_I64) { if (rank) ETB_SMALL(long long, 1); else ETB_SMALL(long long, 0); }
                 else { if (rank) ETB_SMALL(int, 1); else ETB_SMALL(int, 0); }
@@ -249,18 +249,18 @@ int32_t index_impl(void* ws, size_t ws_bytes, const etb_update_item* items, int3
             // K4b: bucket heads per tile
             P.kin = keys[fin];
             P.vin = vals[fin];
-            if (L.key_bytes == 4) ix_count_heads_kernel<uint32_t><<<P.rec_tiles, kIxThreads, 0, stream>>>(P);
-            else ix_count_heads_kernel<uint64_t><<<P.rec_tiles, kIxThreads, 0, stream>>>(P);
+            if (L.key_bytes == 4) launch_k(ix_count_heads_kernel<uint32_t>, P.rec_tiles, kIxThreads, 0, stream, P);
+            else launch_k(ix_count_heads_kernel<uint64_t>, P.rec_tiles, kIxThreads, 0, stream, P);
             ETB_LAUNCHED();
         }
         if (!rec_inline) {
-            ix_scan_counts_kernel<<<1, 1024, 0, stream>>>((uint32_t*)(base + L.off_rec_counts), (int)L.rec_tiles, nnz);
+            launch_k(ix_scan_counts_kernel, 1, 1024, 0, stream, (uint32_t*)(base + L.off_rec_counts), (int)L.rec_tiles, nnz);
             ETB_LAUNCHED();
         }
         for (IxParams& P : groups) {  // one record per bucket head, numbered over the whole call
             if (P.ntiles == 0) continue;
-            if (L.key_bytes == 4) ix_write_records_kernel<uint32_t><<<P.rec_tiles, kIxThreads, 0, stream>>>(P);
-            else ix_write_records_kernel<uint64_t><<<P.rec_tiles, kIxThreads, 0, stream>>>(P);
+            if (L.key_bytes == 4) launch_k(ix_write_records_kernel<uint32_t>, P.rec_tiles, kIxThreads, 0, stream, P);
+            else launch_k(ix_write_records_kernel<uint64_t>, P.rec_tiles, kIxThreads, 0, stream, P);
             ETB_LAUNCHED();
         }
     }

@@ -148,6 +148,7 @@ __device__ __forceinline__ KeyT ix_load_key(const IxItem& it, const KeyT* kin, u
 // ------------------------------------------------------------------------------------ per-tile digit counts
 template <typename KeyT, typename SrcT, int THREADS>
 __global__ void __launch_bounds__(THREADS) ix_hist_kernel(const __grid_constant__ IxParams P) {
+    pdl_begin();
     __shared__ uint32_t cnt[kIxMaxBins];
     constexpr uint32_t kTile = THREADS * kIxItems;
     const int nb = 1 << P.width[P.pass], shift = P.shift[P.pass];
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(THREADS) ix_hist_kernel(const __grid_constant_
 // one thread per (table, digit): exclusive scan of the digit's counts over the table's tiles (in place; consecutive
 // threads = consecutive digits, so every access is coalesced) and the table's total
 __global__ void __launch_bounds__(256) ix_scan_kernel(const __grid_constant__ IxParams P, int tile_size) {
+    pdl_begin();
     const int nb = 1 << P.width[P.pass];
     const int d = blockIdx.x * 256 + threadIdx.x;
     if (d >= nb) return;
@@ -204,6 +206,7 @@ __global__ void __launch_bounds__(256) ix_scan_kernel(const __grid_constant__ Ix
 // tiles per shuffle scan.  The accesses are not coalesced (the counts come from L2, written by ix_hist_kernel just
 // before), so the thread-per-digit kernel stays for ensembles (C2: 0.350 vs 0.368 ms).
 __global__ void __launch_bounds__(256) ix_scan_warp_kernel(const __grid_constant__ IxParams P, int tile_size) {
+    pdl_begin();
     const int nb = 1 << P.width[P.pass];
     const int lane = threadIdx.x & 31;
     const int d = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -326,6 +329,7 @@ __device__ __forceinline__ void ix_rank_rows(const KeyT (&k)[kIxItems], uint32_t
 
 template <typename KeyT, typename SrcT, int RANK, int THREADS>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 4 : 2) ix_scatter_kernel(const __grid_constant__ IxParams P) {
+    pdl_begin();
     constexpr bool kFirst = !std::is_void<SrcT>::value;
     constexpr int kIxThreads = THREADS, kIxWarps = THREADS / 32, kIxTile = THREADS * kIxItems;  // shadow the record kernels' constants
     constexpr int kIxMaxBpt = kIxMaxBins / THREADS;  // digits per thread in the per-digit steps
@@ -458,6 +462,7 @@ constexpr size_t ix_small_smem(int nb) {
 
 template <typename KeyT, typename SrcT, int RANK>
 __global__ void __launch_bounds__(kIxThreads) ix_small_kernel(const __grid_constant__ IxParams P, int npasses) {
+    pdl_begin();
     constexpr int kMaxBpt = kIxMaxBins / kIxThreads;
     extern __shared__ __align__(16) unsigned char ix_smem[];
     const int nb_max = 1 << P.width[0];
@@ -583,6 +588,7 @@ __device__ __forceinline__ uint32_t ix_head_flags(const KeyT* __restrict__ keys,
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kIxThreads) ix_count_heads_kernel(const __grid_constant__ IxParams P) {
+    pdl_begin();
     __shared__ uint32_t warp_sums[kIxWarps];
     const int item = ix_find_item<true>(P, blockIdx.x);
     const IxItem& it = P.item[item];
@@ -602,6 +608,7 @@ __global__ void __launch_bounds__(kIxThreads) ix_count_heads_kernel(const __grid
 
 // exclusive scan of the tile counts of the whole call in place (one block of 1024 threads), total -> nnz
 __global__ void __launch_bounds__(1024) ix_scan_counts_kernel(uint32_t* __restrict__ counts, int ntiles, int64_t* __restrict__ nnz) {
+    pdl_begin();
     __shared__ uint32_t warp_tot[32];
     const int per = (ntiles + 1023) / 1024;
     const int lo = min((int)threadIdx.x * per, ntiles), hi = min(lo + per, ntiles);
@@ -636,6 +643,7 @@ __global__ void __launch_bounds__(1024) ix_scan_counts_kernel(uint32_t* __restri
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kIxThreads) ix_write_records_kernel(const __grid_constant__ IxParams P) {
+    pdl_begin();
     __shared__ uint32_t cnt[kIxItems][kIxWarps];  // heads per (item row, warp), then exclusive offsets
     __shared__ uint32_t warp_sums[kIxWarps];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

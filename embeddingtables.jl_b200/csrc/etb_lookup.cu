@@ -73,6 +73,7 @@ __device__ __forceinline__ double additive_identity<double>() {
 template <typename T, int VB, int VPL, typename IdxT, bool DEEP>
 __global__ void __launch_bounds__(kThreads, (VPL == 1 && !DEEP) ? (sizeof(T) == 4 ? 8 : 5) : (VPL <= 2 ? 4 : 3))
 pooled_kernel(const __grid_constant__ LookupParams P) {
+    pdl_begin();
     constexpr int U = (VPL == 1 && !DEEP) ? 4 : ((8 / VPL) > 1 ? (8 / VPL) : 1);  // row loads in flight per lane batch
     using V = Vec<T, VB>;
     using A = AccVec<T, VB>;  // == V except for half-precision tables (Float32 accumulation)
@@ -147,6 +148,7 @@ pooled_kernel(const __grid_constant__ LookupParams P) {
 template <typename T, int VPL, typename IdxT, int BAG, int C>
 __global__ void __launch_bounds__(kThreads)
 pooled_smallbag_kernel(const __grid_constant__ LookupParams P) {
+    pdl_begin();
     constexpr int VB = 16;
     using V = Vec<T, VB>;
     const LookupDesc& d = P.item[blockIdx.y];
@@ -194,6 +196,7 @@ pooled_smallbag_kernel(const __grid_constant__ LookupParams P) {
 template <int VB, int VPL, typename IdxT>
 __global__ void __launch_bounds__(kThreads)
 gather_kernel(const __grid_constant__ LookupParams P) {
+    pdl_begin();
     using V = Vec<uint32_t, VB>;
     const LookupDesc& d = P.item[blockIdx.y];
     const int G = P.G;
@@ -281,11 +284,11 @@ template <typename T, int VB, typename IdxT>
 static cudaError_t launch_pooled_vpl(int vpl, dim3 grid, cudaStream_t s, const LookupParams& P) {
     switch (vpl) {
         case 1:
-            if (P.G == 32) pooled_kernel<T, VB, 1, IdxT, false><<<grid, kThreads, 0, s>>>(P);
-            else pooled_kernel<T, VB, 1, IdxT, true><<<grid, kThreads, 0, s>>>(P);
+            if (P.G == 32) launch_k(pooled_kernel<T, VB, 1, IdxT, false>, grid, kThreads, 0, s, P);
+            else launch_k(pooled_kernel<T, VB, 1, IdxT, true>, grid, kThreads, 0, s, P);
             break;
-        case 2: pooled_kernel<T, VB, 2, IdxT, true><<<grid, kThreads, 0, s>>>(P); break;
-        default: pooled_kernel<T, VB, 4, IdxT, true><<<grid, kThreads, 0, s>>>(P); break;
+        case 2: launch_k(pooled_kernel<T, VB, 2, IdxT, true>, grid, kThreads, 0, s, P); break;
+        default: launch_k(pooled_kernel<T, VB, 4, IdxT, true>, grid, kThreads, 0, s, P); break;
     }
     return cudaGetLastError();
 }
@@ -309,7 +312,7 @@ static int launch_smallbag_t(const LookupClass& c, int bag, uint32_t max_batch, 
 #define ETB_SB(VPLV, BAGV, CV)                                                                          \
     if (c.vpl == VPLV && bag == BAGV && CV * BAGV <= c.G) {                                             \
         dim3 grid((max_batch + groups * CV - 1) / (groups * CV), (unsigned)n, 1);                       \
-        pooled_smallbag_kernel<T, VPLV, IdxT, BAGV, CV><<<grid, kThreads, 0, s>>>(P);                   \
+        launch_k(pooled_smallbag_kernel<T, VPLV, IdxT, BAGV, CV>, grid, kThreads, 0, s, P);                   \
         *err = cudaGetLastError();                                                                      \
         return CV;                                                                                      \
     }
@@ -347,9 +350,9 @@ static cudaError_t launch_pooled(const LookupClass& c, dim3 grid, cudaStream_t s
 template <int VB, typename IdxT>
 static cudaError_t launch_gather_vpl(int vpl, dim3 grid, cudaStream_t s, const LookupParams& P) {
     switch (vpl) {
-        case 1: gather_kernel<VB, 1, IdxT><<<grid, kThreads, 0, s>>>(P); break;
-        case 2: gather_kernel<VB, 2, IdxT><<<grid, kThreads, 0, s>>>(P); break;
-        default: gather_kernel<VB, 4, IdxT><<<grid, kThreads, 0, s>>>(P); break;
+        case 1: launch_k(gather_kernel<VB, 1, IdxT>, grid, kThreads, 0, s, P); break;
+        case 2: launch_k(gather_kernel<VB, 2, IdxT>, grid, kThreads, 0, s, P); break;
+        default: launch_k(gather_kernel<VB, 4, IdxT>, grid, kThreads, 0, s, P); break;
     }
     return cudaGetLastError();
 }

@@ -2,6 +2,8 @@
 // that replaces Julia `Array` storage for tables, plus error reporting.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "etb_common.cuh"
 
 namespace etb {
@@ -22,6 +24,11 @@ int32_t fail(int32_t status, const char* fmt, ...) {
 int32_t& launch_counter() {
     static thread_local int32_t n = 0;
     return n;
+}
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("ETB_PDL"); return e && e[0] == '1'; }();
+    return on;
 }
 
 int num_sms() {

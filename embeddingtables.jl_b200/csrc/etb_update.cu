@@ -239,6 +239,7 @@ struct alignas(16) TileMeta2 {
 template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads, ETB_UPDATE_MIN_BLOCKS)
 sgd_update_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     constexpr int UB = (ETB_UPDATE_UB / VPL) > 1 ? (ETB_UPDATE_UB / VPL) : 1;  // buckets in flight per group
     constexpr int U = (ETB_UPDATE_U / VPL) > 1 ? (ETB_UPDATE_U / VPL) : 1;  // extra member rows in flight
     constexpr int RPL = ETB_UPDATE_RPL;                                       // records (buckets) per lane
@@ -383,6 +384,7 @@ sgd_update_kernel(const __grid_constant__ UpdParams P) {
 template <typename T, int VPL, int G, int UB, int OPT>
 __global__ void __launch_bounds__(kUThreads, ETB_UPDATE_EXACT_MIN_BLOCKS)
 sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     constexpr int VB = 16;
     using V = Vec<T, VB>;
     __shared__ TileMeta s_meta[kUThreads];
@@ -521,6 +523,7 @@ sgd_update_exact_kernel(const __grid_constant__ UpdParams P) {
 template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads, 2)  // up to 128 registers: a spill of loaded rows serialises the loads
 bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
     using V = Vec<T, VB>;
     const int G = P.G, nvec = P.nvec;
@@ -604,6 +607,7 @@ bucket_tasks_kernel(const __grid_constant__ UpdParams P) {
 template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads)
 long_combine_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     constexpr int U = (8 / VPL) > 1 ? (8 / VPL) : 1;
     using V = Vec<T, VB>;
     using A = AccVec<T, VB>;
@@ -725,6 +729,7 @@ __device__ __forceinline__ void lds_vec(void* out, const char* p) {
 template <typename T, int VB, int VPL, int OPT>
 __global__ void __launch_bounds__(kUThreads)
 long_strict_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     using V = Vec<T, VB>;
     using A = AccVec<T, VB>;
     extern __shared__ __align__(16) char s_rows[];  // [kStrictStages][rows_per_stage][nvec * VB]
@@ -947,6 +952,7 @@ __device__ __forceinline__ void lds_elem(T* out, const char* p) {  // volatile: 
 template <typename T, int VB>
 __global__ void __launch_bounds__(kUThreads)
 long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     using A = acc_t<T>;
     extern __shared__ __align__(16) char s_rows[];  // [S][R][SB]
     constexpr int kProducers = kUThreads - 32;
@@ -1128,6 +1134,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32
 template <typename T, int VPL, int OPT>
 __global__ void __launch_bounds__(kBulkThreads)
 long_strict_bulk_kernel(const __grid_constant__ UpdParams P) {
+    pdl_begin();
     constexpr int VB = 16;
     using V = Vec<T, VB>;
     using A = AccVec<T, VB>;
@@ -1316,8 +1323,8 @@ static bool strict_sliced() {
 
 template <typename T, int VB, int VPL, int OPT>
 static void launch_update_one(int which, int grid, cudaStream_t s, const UpdParams& P) {
-    if (which == kKernelMain) sgd_update_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
-    else if (which == kKernelTasks) bucket_tasks_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
+    if (which == kKernelMain) launch_k(sgd_update_kernel<T, VB, VPL, OPT>, grid, kUThreads, 0, s, P);
+    else if (which == kKernelTasks) launch_k(bucket_tasks_kernel<T, VB, VPL, OPT>, grid, kUThreads, 0, s, P);
     else if (which == kKernelStrictLong && VB == 16 && P.nvec * VB * kBulkRows * kBulkStages <= 200 * 1024 &&
              getenv("ETB_STRICT_BULK")) {  // measured 2x slower than the cp.async variant for 512-byte rows: opt-in only
         if constexpr (VB == 16) {  // the bulk-copy (TMA) variant
@@ -1327,7 +1334,7 @@ static void launch_update_one(int which, int grid, cudaStream_t s, const UpdPara
                 cudaFuncSetAttribute(long_strict_bulk_kernel<T, VPL, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                 configured = smem;
             }
-            long_strict_bulk_kernel<T, VPL, OPT><<<grid, kBulkThreads, smem, s>>>(P);
+            launch_k(long_strict_bulk_kernel<T, VPL, OPT>, grid, kBulkThreads, smem, s, P);
         }
     } else if (which == kKernelStrictLong && P.strict_long == 2) {  // the feature-sliced kernel (SGD)
         constexpr int kSmem = kSliceStages * kSliceStageBytes;  // 64 KB of dynamic shared memory: three CTAs per SM
@@ -1336,7 +1343,7 @@ static void launch_update_one(int which, int grid, cudaStream_t s, const UpdPara
             cudaFuncSetAttribute(long_strict_sliced_kernel<T, VB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
             configured = true;
         }
-        long_strict_sliced_kernel<T, VB><<<grid, kUThreads, kSmem, s>>>(P);
+        launch_k(long_strict_sliced_kernel<T, VB>, grid, kUThreads, kSmem, s, P);
     } else if (which == kKernelStrictLong) {
         constexpr int kSmem = kStrictStages * kStrictStageBytes;  // 96 KB of dynamic shared memory: opt in once
         static thread_local bool configured = false;
@@ -1344,8 +1351,8 @@ static void launch_update_one(int which, int grid, cudaStream_t s, const UpdPara
             cudaFuncSetAttribute(long_strict_kernel<T, VB, VPL, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
             configured = true;
         }
-        long_strict_kernel<T, VB, VPL, OPT><<<grid, kUThreads, kSmem, s>>>(P);
-    } else long_combine_kernel<T, VB, VPL, OPT><<<grid, kUThreads, 0, s>>>(P);
+        launch_k(long_strict_kernel<T, VB, VPL, OPT>, grid, kUThreads, kSmem, s, P);
+    } else launch_k(long_combine_kernel<T, VB, VPL, OPT>, grid, kUThreads, 0, s, P);
 }
 
 template <typename T, int VB, int OPT>
@@ -1373,7 +1380,7 @@ static bool launch_update_exact(const UpdClass& c, int grid, cudaStream_t s, con
     if (sizeof(T) == 2 && c.vpl > 1) return false;           // half types: 8 accumulators per vector, VPL > 1 would spill
 #define ETB_EXACT(VPLV, GV, UBV)                                                         \
     if (c.vpl == VPLV && c.G == GV) {                                                    \
-        sgd_update_exact_kernel<T, VPLV, GV, (UBV), OPT><<<grid, kUThreads, 0, s>>>(P);  \
+        launch_k(sgd_update_exact_kernel<T, VPLV, GV, (UBV), OPT>, grid, kUThreads, 0, s, P);  \
         return true;                                                                     \
     }
     ETB_EXACT(1, 32, UB) ETB_EXACT(1, 16, UB) ETB_EXACT(1, 8, UB) ETB_EXACT(1, 4, UB < 4 ? UB : 4)
@@ -1519,6 +1526,7 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
 template <typename T, typename IdxT>
 __global__ void uncompress_kernel(T* dst, int64_t ld_dst, int dim, const T* delta, int64_t ld_delta, const IdxT* idx,
                                   int64_t bag, int64_t batch, int64_t ld_idx) {
+    pdl_begin();
     // one thread per feature element walks every occurrence in order: deterministic, and the
     // same association as the reference's `columnview(dst, c) .+= update` loop
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1544,6 +1552,7 @@ struct A2ABlocks {
 template <int VB, bool UNPACK>
 __global__ void __launch_bounds__(256)
 a2a_copy_kernel(char* strided, int64_t ld_bytes, const __grid_constant__ A2ABlocks B, int64_t batch_local, int es) {
+    pdl_begin();
     const int r = blockIdx.y;
     const int64_t row_bytes = B.rows[r] * es;
     const int64_t vec_per_col = row_bytes / VB;
@@ -1591,8 +1600,8 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, voi
     dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8), (unsigned)nranks);
     const int64_t ldb = ld * es;
 #define ETB_A2A(VBV)                                                                                          \
-    if (unpack) a2a_copy_kernel<VBV, true><<<grid, 256, 0, stream>>>((char*)strided, ldb, B, batch_local, es); \
-    else a2a_copy_kernel<VBV, false><<<grid, 256, 0, stream>>>((char*)strided, ldb, B, batch_local, es);
+    if (unpack) launch_k(a2a_copy_kernel<VBV, true>, grid, 256, 0, stream, (char*)strided, ldb, B, batch_local, es); \
+    else launch_k(a2a_copy_kernel<VBV, false>, grid, 256, 0, stream, (char*)strided, ldb, B, batch_local, es);
     if (vb == 16) { ETB_A2A(16) } else if (vb == 8) { ETB_A2A(8) } else { ETB_A2A(4) }
 #undef ETB_A2A
     ETB_LAUNCHED();
@@ -1623,6 +1632,7 @@ struct CacheParams {
 
 // occurrence counts (clamped to the last bin) of the rows of host-tier tables that are not cached yet
 __global__ void __launch_bounds__(256) cache_count_kernel(const __grid_constant__ CacheParams P) {
+    pdl_begin();
     const int64_t nnz = *P.nnz;
     for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < nnz; b += (int64_t)gridDim.x * 256) {
         const BucketRec rec = P.recs[b];
@@ -1649,6 +1659,7 @@ __device__ __forceinline__ int cache_threshold(const CacheItem& c, int min_count
 }
 
 __global__ void __launch_bounds__(256) cache_admit_kernel(const __grid_constant__ CacheParams P) {
+    pdl_begin();
     __shared__ int s_threshold[kUMaxItems];
     for (int i = threadIdx.x; i < P.n_items; i += 256)
         s_threshold[i] = P.item[i].slot_of_row ? cache_threshold(P.item[i], P.min_count) : 0x7fffffff;
@@ -1691,6 +1702,7 @@ __global__ void __launch_bounds__(256) cache_admit_kernel(const __grid_constant_
 
 // write every cached row back to the host table: one warp per slot
 __global__ void __launch_bounds__(256) cache_flush_kernel(CacheItem c) {
+    pdl_begin();
     const int lane = threadIdx.x & 31;
     const int used = min(*c.cursor, c.capacity);
     for (int s = blockIdx.x * 8 + (threadIdx.x >> 5); s < used; s += gridDim.x * 8) {
@@ -1725,6 +1737,7 @@ static bool make_cache_item(const etb_table& t, CacheItem& c) {
 // have completed, so their peer stores are ordered before the flag; the kernels after it see every peer's data.
 struct PeerFlags { uint32_t* flags[16]; };
 __global__ void peer_barrier_kernel(const __grid_constant__ PeerFlags F, int me, int nranks, uint32_t epoch) {
+    pdl_begin();
     const int r = threadIdx.x;
     if (r < nranks) {
         __threadfence_system();
@@ -1779,11 +1792,11 @@ int32_t etb_uncompress(void* dst, int64_t ld_dst, int32_t dim, int32_t elt, cons
     const int threads = 128, blocks = (dim + threads - 1) / threads;
     cudaStream_t s = (cudaStream_t)stream;
     if (elt == ETB_F32) {
-        if (idx_elt == ETB_I64) uncompress_kernel<float, long long><<<blocks, threads, 0, s>>>((float*)dst, ld_dst, dim, (const float*)delta, ld_delta, (const long long*)idx, bag, batch, ld_idx);
-        else uncompress_kernel<float, int><<<blocks, threads, 0, s>>>((float*)dst, ld_dst, dim, (const float*)delta, ld_delta, (const int*)idx, bag, batch, ld_idx);
+        if (idx_elt == ETB_I64) launch_k(uncompress_kernel<float, long long>, blocks, threads, 0, s, (float*)dst, ld_dst, dim, (const float*)delta, ld_delta, (const long long*)idx, bag, batch, ld_idx);
+        else launch_k(uncompress_kernel<float, int>, blocks, threads, 0, s, (float*)dst, ld_dst, dim, (const float*)delta, ld_delta, (const int*)idx, bag, batch, ld_idx);
     } else {
-        if (idx_elt == ETB_I64) uncompress_kernel<double, long long><<<blocks, threads, 0, s>>>((double*)dst, ld_dst, dim, (const double*)delta, ld_delta, (const long long*)idx, bag, batch, ld_idx);
-        else uncompress_kernel<double, int><<<blocks, threads, 0, s>>>((double*)dst, ld_dst, dim, (const double*)delta, ld_delta, (const int*)idx, bag, batch, ld_idx);
+        if (idx_elt == ETB_I64) launch_k(uncompress_kernel<double, long long>, blocks, threads, 0, s, (double*)dst, ld_dst, dim, (const double*)delta, ld_delta, (const long long*)idx, bag, batch, ld_idx);
+        else launch_k(uncompress_kernel<double, int>, blocks, threads, 0, s, (double*)dst, ld_dst, dim, (const double*)delta, ld_delta, (const int*)idx, bag, batch, ld_idx);
     }
     ETB_LAUNCHED();
     return ETB_OK;
@@ -1836,9 +1849,9 @@ int32_t etb_cache_admit(const etb_index_view* view_host, const etb_update_item* 
         for (int j = 0; j < n; ++j)
             if (P.item[j].hist) ETB_CUDA(cudaMemsetAsync(P.item[j].hist, 0, ETB_CACHE_HIST_BINS * sizeof(int32_t), (cudaStream_t)stream));
         const int grid = (int)std::min<int64_t>((view_host->n_total + 7) / 8, (int64_t)num_sms() * 8);
-        cache_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        launch_k(cache_count_kernel, grid, 256, 0, (cudaStream_t)stream, P);
         ETB_LAUNCHED();
-        cache_admit_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P);
+        launch_k(cache_admit_kernel, grid, 256, 0, (cudaStream_t)stream, P);
         ETB_LAUNCHED();
     }
     return ETB_OK;
@@ -1853,7 +1866,7 @@ int32_t etb_cache_flush(const etb_table* table_host, void* stream) {
     ETB_REQUIRE(make_cache_item(*table_host, c), "etb_cache_flush: not an ETB_TABLE_CACHED table");
     if (c.capacity == 0) return ETB_OK;
     const int grid = std::min((c.capacity + 7) / 8, num_sms() * 8);
-    cache_flush_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(c);
+    launch_k(cache_flush_kernel, grid, 256, 0, (cudaStream_t)stream, c);
     ETB_LAUNCHED();
     return ETB_OK;
 }
@@ -1875,7 +1888,7 @@ int32_t etb_peer_barrier(void* const* flag_ptrs_host, int32_t rank, int32_t nran
     PeerFlags F;
     for (int r = 0; r < 16; ++r) F.flags[r] = r < nranks ? (uint32_t*)flag_ptrs_host[r] : nullptr;
     for (int r = 0; r < nranks; ++r) ETB_REQUIRE(F.flags[r], "etb_peer_barrier: null flag array of rank %d", r);
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(F, rank, nranks, epoch);
+    launch_k(peer_barrier_kernel, 1, 32, 0, (cudaStream_t)stream, F, rank, nranks, epoch);
     ETB_LAUNCHED();
     return ETB_OK;
 }

@@ -350,18 +350,26 @@ class ShardedEnsemble:
         per = bag * p.batch_global
         return [DeviceArray(glob, shape, t * per, None, np_dtype) for t in range(t_mine)]
 
+    def prefetch_index(self):
+        """index! of my tables for the indices of the last forward(), on the side stream, starting behind whatever the
+        current stream holds so far.  forward() calls it before the lookup (index! then runs beside the lookup, both
+        HBM-bound); called after forward(..., prefetch_index=False) it runs beside the backward exchange instead, which
+        is NVLink-bound and leaves HBM idle."""
+        p = self.plan
+        self.index_launches = 0
+        b = self.group_bounds[p.rank]
+        for g, ix in enumerate(self.group_indexers):
+            a0, a1 = (b[g], b[g + 1]) if self.n_groups > 1 else (0, len(self.tables))
+            _prefetch_index(ix, self.tables[a0:a1], self._I[a0:a1])
+            self.index_launches += _lib.lib().etb_last_launch_count()
+
     def forward(self, I, out: DeviceArray = None, prefetch_index: bool = True, cols=None) -> DeviceArray:
         p = self.plan
         Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else
                                              [I.lastdim(t) for t in range(I.shape[-1])])]
         self._I = Is
         if prefetch_index:   # index! needs only the indices: run it beside the lookup and the exchange
-            self.index_launches = 0
-            b = self.group_bounds[p.rank]
-            for g, ix in enumerate(self.group_indexers):
-                a0, a1 = (b[g], b[g + 1]) if self.n_groups > 1 else (0, len(self.tables))
-                _prefetch_index(ix, self.tables[a0:a1], Is[a0:a1])
-                self.index_launches += _lib.lib().etb_last_launch_count()
+            self.prefetch_index()
         if self.fused:
             assert out is None, "fused mode writes into the peer-mapped self.out"
             if self.copy_engine and cols is None:

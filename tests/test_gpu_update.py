@@ -507,3 +507,31 @@ def test_host_mapped_result_and_cotangent(E, O):
         ref = O.Table(base[k].copy(order="F"), static=True)
         O.update(ref, np.asfortranarray(delta_h[16 + 64 * k:16 + 64 * (k + 1)]), I[:, :, k], 0.5)
         assert np.array_equal(tables[k].to_numpy(), ref.data)
+
+
+def test_heterogeneous_split_ensemble(E, O, order):
+    # chunked tables of very different row counts, mixed with plain tables and two feature sizes (two kernel classes), bucket
+    # count not a multiple of 32, and hot rows (long buckets on chunked tables): a lane that does not own a bucket
+    # must never resolve a row through another table's chunk-pointer array
+    rng = np.random.default_rng(77)
+    spec = [("split", 64, 1000, 130), ("split", 64, 50, 7), ("simple", 16, 300, 0), ("split", 16, 2000, 512),
+            ("split", 64, 9, 2), ("simple", 64, 4000, 0)]
+    batch, bag = 333, 3
+    base = [rng.standard_normal((dim, nrows)).astype(np.float32) for _, dim, nrows, _ in spec]
+    tables = [E.SplitEmbedding(b.copy(), chunk) if kind == "split" else E.SimpleEmbedding(b.copy())
+              for b, (kind, _, _, chunk) in zip(base, spec)]
+    I = [rng.integers(1, nrows + 1, (bag, batch)) for _, _, nrows, _ in spec]
+    I[0][rng.random(I[0].shape) < 0.5] = 999          # a hot row in the last chunk of the first table
+    I[4][:] = rng.integers(8, 10, I[4].shape)          # two rows take everything
+    deltas = [rng.standard_normal((dim, batch)).astype(np.float32) for _, dim, _, _ in spec]
+    grads = [E.SparseEmbeddingUpdate(t.lookup_type, d, i) for t, d, i in zip(tables, deltas, I)]
+    E.update_(E.Descent(0.05), tables, grads, [E.Indexer()])
+    for t, b, d, i, (kind, _, _, chunk) in zip(tables, base, deltas, I, spec):
+        # SplitEmbedding(A, cols_per_shard) is Static{featuresize} like the reference's (src/split.jl:9-27): FMA epilogue
+        ref = O.Table(b.copy(order="F"), static=True, cols_per_shard=chunk) if kind == "split" else O.Table(b.copy(order="F"))
+        O.update(ref, d, i, 0.05)
+        got, want = t.to_numpy(), (ref.dense() if kind == "split" else ref.data)
+        if order == "strict":
+            assert np.array_equal(got, want)
+        else:
+            assert np.linalg.norm(got - want) <= RTOL * np.linalg.norm(want)
