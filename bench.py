@@ -64,14 +64,18 @@ def make_indices(rng, dist, nt, nrows, bag, batch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  nvidia-smi needs seconds
+    for its first sample on an 8-GPU box, so it is started when the process starts (start()); every sample carries
+    nvidia-smi's own timestamp and only those between mark_begin() and stop() -- warm-up, timed region, per-phase pass
+    and e2e region -- are reported."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
-        self.device, self.proc = device, None
+        self.device, self.proc, self.t_begin = device, None, None
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
 
-    def __enter__(self):
+    def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "20", "-i", str(self.device)], stdout=subprocess.PIPE,
@@ -80,33 +84,52 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def mark_begin(self):
+        import datetime
+        self.t_begin = datetime.datetime.now()
+
+    def __enter__(self):          # start + mark in one go (single-process callers that create the sampler late)
+        if self.proc is None:
+            self.start()
+        self.mark_begin()
+        return self
+
     def __exit__(self, *a):
-        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.stop()
+
+    def stop(self):
+        import datetime
         if self.proc is None:
             return
         time.sleep(0.15)
+        t_end = datetime.datetime.now()
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             return
-        sm, mx, reasons = [], [], set()
+        self.proc = None
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[2]), float(f[3]), {n for n, v in zip(names, f[6:10]) if v.lower() == "active"}))
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower() == "active":
-                    reasons.add(name)
-        if sm:
-            self.result = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                           "samples": len(sm)}
+        lo = (self.t_begin or t_end) - datetime.timedelta(milliseconds=50)
+        window = [r for r in rows if lo <= r[0] <= t_end]
+        where = "timed regions"
+        if not window and rows:   # clock skew between nvidia-smi's stamps and ours, or a sampling gap: the newest samples
+            window, where = rows[-10:], "last samples before the end of the timed regions"
+        if window:
+            reasons = set().union(*[r[3] for r in window])
+            self.result = {"sm_mhz": float(np.median([r[1] for r in window])), "sm_max_mhz": float(max(r[2] for r in window)),
+                           "reasons": sorted(reasons), "samples": len(window), "window": where}
 
 
 def common_config(world, dist):
@@ -218,6 +241,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    args._clocks = ClockSampler(local).start()   # sampling from now on; the report keeps the timed regions' samples
     args._numa = bind_to_gpu_numa(local) if (world > 1 or os.environ.get("ETB_BIND_NUMA")) else None
     E._lib.check(E.lib().etb_init(local))
     if world > 1:
@@ -363,8 +387,8 @@ def run_ours(args):
     overlap = not args.no_overlap
     # nvidia-smi needs up to a second to deliver its first sample: start it before the warm-up so that it is
     # sampling (every 20 ms) throughout the timed regions; stopped after the e2e region
-    clocks = ClockSampler(local)
-    clocks.__enter__()
+    clocks = args._clocks
+    clocks.mark_begin()
     for _ in range(args.warmup):
         step(overlap=False)
         step(overlap=overlap)
@@ -404,7 +428,7 @@ def run_ours(args):
     sync()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / K
     e2e_ms = max(e0.elapsed_time(e1) / K, e2e_wall_ms)  # host-side work counts too
-    clocks.__exit__(None, None, None)
+    clocks.stop()
 
     # ---- roofline of the dominant kernel ---------------------------------------------------
     peak, peak_src = measured_peak_gbs()
@@ -664,8 +688,8 @@ def run_sharded(args, rank, world, local):
         dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local)   # started before the warm-up (nvidia-smi needs ~1 s for its first sample),
-    clocks.__enter__()             # stopped after the e2e region
+    clocks = args._clocks          # sampling since the process started; stopped after the e2e region
+    clocks.mark_begin()
     for _ in range(args.warmup):
         step()
     sync()
@@ -702,7 +726,7 @@ def run_sharded(args, rank, world, local):
     e1.record()
     sync()
     e2e = torch.tensor([max(e0.elapsed_time(e1) / K, (time.perf_counter() - t0) * 1e3 / K)], device="cuda", dtype=torch.float64)
-    clocks.__exit__(None, None, None)
+    clocks.stop()
     dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
     e2e_ms = e2e.item()
 
