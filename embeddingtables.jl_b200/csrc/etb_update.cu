@@ -1549,23 +1549,38 @@ struct A2ABlocks {
     char* dense[16];  // block r's (rows[r] x batch_local) matrix: local buffer or peer memory
 };
 
+// One CTA walks whole columns of block r (blockIdx.y): a column of the block is one contiguous run on both sides, so
+// there is no division per vector, and a thread has up to four 16-byte loads in flight before its first store (the
+// stores go over NVLink when the destination is peer memory).
 template <int VB, bool UNPACK>
 __global__ void __launch_bounds__(256)
 a2a_copy_kernel(char* strided, int64_t ld_bytes, const __grid_constant__ A2ABlocks B, int64_t batch_local, int es) {
     pdl_begin();
+    constexpr int U = 4;
     const int r = blockIdx.y;
     const int64_t row_bytes = B.rows[r] * es;
-    const int64_t vec_per_col = row_bytes / VB;
-    const int64_t total = vec_per_col * batch_local;
+    const int vec_per_col = (int)(row_bytes / VB);
     char* dbase = B.dense[r];
     char* sbase = strided + B.row_off[r] * es;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t col = t / vec_per_col, v = t - col * vec_per_col;
-        char* s = sbase + col * ld_bytes + v * VB;
-        char* d = dbase + col * B.dense_ld_bytes[r] + v * VB;
-        Vec<uint32_t, VB> x;
-        if (UNPACK) { ld_row<VB>(&x, d); st_stream<VB>(s, &x); }
-        else { ld_row<VB>(&x, s); st_stream<VB>(d, &x); }
+    const int64_t dld = B.dense_ld_bytes[r];
+    // L threads per column (a power of two, at most the CTA): narrow blocks put several columns side by side
+    int L = 256;
+    while (L > 1 && (L >> 1) >= vec_per_col) L >>= 1;
+    const int cpi = 256 / L, cl = threadIdx.x / L, vl = threadIdx.x & (L - 1);
+    for (int64_t col = (int64_t)blockIdx.x * cpi + cl; col < batch_local; col += (int64_t)gridDim.x * cpi) {
+        char* s = sbase + col * ld_bytes;
+        char* d = dbase + col * dld;
+        char* from = UNPACK ? d : s;
+        char* to = UNPACK ? s : d;
+        for (int v0 = vl; v0 < vec_per_col; v0 += U * L) {
+            Vec<uint32_t, VB> x[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (v0 + u * L < vec_per_col) ld_row<VB>(&x[u], from + (int64_t)(v0 + u * L) * VB);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (v0 + u * L < vec_per_col) st_stream<VB>(to + (int64_t)(v0 + u * L) * VB, &x[u]);
+        }
     }
 }
 
@@ -1596,8 +1611,10 @@ static int32_t a2a_copy(bool unpack, void* strided, int64_t ld, void* dense, voi
     while (vb > es && ((ld * es) % vb || (uintptr_t)strided % vb)) vb >>= 1;
     if (vb < 4) return fail(ETB_ERR_UNSUPPORTED, "etb_a2a: half-precision blocks must be 4-byte aligned (even row counts and offsets)");
     if (max_rows == 0) return ETB_OK;
-    const int64_t total = max_rows * es / vb * batch_local;
-    dim3 grid((unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)num_sms() * 8), (unsigned)nranks);
+    int lanes = 256;  // threads per column of the widest block (the kernel derives each block's own)
+    while (lanes > 1 && (lanes >> 1) >= max_rows * es / vb) lanes >>= 1;
+    const int64_t col_groups = (batch_local + 256 / lanes - 1) / (256 / lanes);
+    dim3 grid((unsigned)std::min<int64_t>(col_groups, (int64_t)num_sms() * 8), (unsigned)nranks);
     const int64_t ldb = ld * es;
 #define ETB_A2A(VBV)                                                                                          \
     if (unpack) launch_k(a2a_copy_kernel<VBV, true>, grid, 256, 0, stream, (char*)strided, ldb, B, batch_local, es); \
