@@ -898,7 +898,7 @@ long_strict_kernel(const __grid_constant__ UpdParams P) {
 #define ETB_SLICE_STAGES 4
 #endif
 #ifndef ETB_SLICE_CTAS
-#define ETB_SLICE_CTAS 4
+#define ETB_SLICE_CTAS 3  /* CTAs per SM of the grid = what fits (73 KB of shared memory, 76 registers): one wave, every job starts at once; 4 measured the same */
 #endif
 #ifndef ETB_SLICE_U
 #define ETB_SLICE_U 16
