@@ -966,7 +966,7 @@ long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
     const int nsl = (dim + kSliceElems - 1) / kSliceElems;
     const int lane = threadIdx.x & 31;
     const bool consumer = threadIdx.x < 32;  // warp 0 adds, warps 1..7 load
-    const uint32_t n_jobs = P.counters->n_long * (uint32_t)nsl;
+    const uint64_t n_jobs = (uint64_t)P.counters->n_long * (uint64_t)nsl;
     const uint64_t row_mask = (P.row_bits >= 64) ? ~0ull : ((1ull << P.row_bits) - 1ull);
     const A eta = (A)P.eta;
     if (threadIdx.x < S) {
@@ -980,14 +980,14 @@ long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
     uint32_t gb = 0;
     uint4 lr_next = make_uint4(0, 0, 0, 0);  // the next job's record is fetched while this job runs
     if (blockIdx.x < n_jobs) lr_next = __ldg((const uint4*)(P.longs + blockIdx.x / (uint32_t)nsl));
-    for (uint32_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
-        const uint32_t j = job / (uint32_t)nsl;
-        const int sl = (int)(job - j * (uint32_t)nsl);
+    for (uint64_t job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+        const uint64_t j = job / (uint64_t)nsl;
+        const int sl = (int)(job - j * (uint64_t)nsl);
         const int sbytes = min(SB, row_bytes - sl * SB);  // this slice's bytes of a row (a multiple of VB)
         const int pps = sbytes / VB;                      // pieces per member row
         const int R = min(min(kSliceMaxRows, kSliceStageBytes / SB), kSlicePieces * kProducers / pps);
         const uint4 lr = lr_next;  // {start, members, key} (register_sliced_long_bucket)
-        if (job + gridDim.x < n_jobs) lr_next = __ldg((const uint4*)(P.longs + (job + gridDim.x) / (uint32_t)nsl));
+        if (job + gridDim.x < n_jobs) lr_next = __ldg((const uint4*)(P.longs + (job + gridDim.x) / (uint64_t)nsl));
         const int64_t start = lr.x;
         const int members = (int)lr.y;
         const uint64_t key = ((uint64_t)lr.w << 32) | lr.z;
@@ -1077,7 +1077,7 @@ long_strict_sliced_kernel(const __grid_constant__ UpdParams P) {
             }
 #ifdef ETB_SLICE_PROFILE
             if (lane == 0 && members > 20000)
-                printf("job %u slice %d members %d batches %d: wait %lld add %lld cycles\n", job, sl, members, nbatch, prof_wait, prof_add);
+                printf("job %llu slice %d members %d batches %d: wait %lld add %lld cycles\n", (unsigned long long)job, sl, members, nbatch, prof_wait, prof_add);
 #endif
             if (on) *mine_row = sgd_apply<T>(old, acc, eta, d.table.pad != 0);
         } else {
