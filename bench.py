@@ -317,7 +317,7 @@ def run_ours(args):
     DUPLEX = os.environ.get("ETB_E2E_DUPLEX", "1") != "0"
     E2E_CHUNKS = max(1, int(os.environ.get("ETB_E2E_CHUNKS", "8" if DUPLEX else "4")))
     E2E_DENSE = min(E2E_CHUNKS - 1, max(0, int(os.environ.get("ETB_E2E_DENSE", str(E2E_CHUNKS // 2))))) if DUPLEX else 0
-    E2E_GROUPS = max(1, min(NT, int(os.environ.get("ETB_E2E_GROUPS", "13"))))
+    E2E_GROUPS = max(1, min(NT, int(os.environ.get("ETB_E2E_GROUPS", "7"))))
     bounds = [round(g * NT / E2E_GROUPS) for g in range(E2E_GROUPS + 1)]
     groups = [(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
     group_ix = [E.Indexer() for _ in groups]

@@ -80,7 +80,7 @@ def main():
     A(f"| Zipf(1.05) indices, strict order (default) | step {z['ms_per_step']:.2f} ms = {z['value'] / 1e9:.2f} G lookups/s (forward {zk['pooled_kernel']['ms']:.2f} ms from L2, update {zk['sgd_update_kernel']['ms']:.2f} ms incl. the hot rows, streamed slice by slice: 3.75 ms before the slicing) | split order: 2.44 ms (`set_update_order(\"split\")`: 2.38 ms now) |\n")
     A("### Launch list of the step (cold-cache, serialised by ncu; compare shares)\n")
     A(launch_table("r2_launches_bench_c2.csv"))
-    A("\n(The list covers the warm-up, timed, per-phase and e2e regions of `bench.py --steps 2 --warmup 3`; the e2e region\nlooks the batch up in 8 column chunks and updates in 13 table groups, hence the smaller launches of the same kernels.)\n")
+    A("\n(The list covers the warm-up, timed, per-phase and e2e regions of `bench.py --steps 2 --warmup 3`; the e2e region\nlooks the batch up in 8 column chunks and updates in 7 table groups, hence the smaller launches of the same kernels.)\n")
     A("### Hot kernels under `ncu --set full` (`r2_ncu_kernels.json`)\n")
     A("| kernel | µs | DRAM read + write | registers | warps/SM | issue slots busy | warp instructions |\n|---|---|---|---|---|---|---|")
     for name, d in nk.items():
