@@ -540,9 +540,14 @@ def run_sharded(args, rank, world, local):
     plan = ShardPlan([DIM] * (NT * world), world, rank, PREPEND, BATCH)
     fused = not args.nccl_a2a
     G = max(1, int(os.environ.get("ETB_TABLE_GROUPS", "1"))) if fused else 1   # measured on 8 GPUs: 1 group 3.64 ms, 2 groups 3.67, 4 groups 4.47
-    ens = ShardedEnsemble(tables, plan, fused=fused, table_groups=G, peer_barrier=not args.nccl_barrier,
+    # the host-buffer (e2e) step always runs by table groups (each group's exchange + update! as its cotangent slice
+    # lands); the device-timed step runs the ensemble whole unless ETB_TABLE_GROUPS asks for groups
+    GE = (G if G > 1 else max(1, int(os.environ.get("ETB_E2E_TABLE_GROUPS", "4")))) if fused else 1
+    ens = ShardedEnsemble(tables, plan, fused=fused, table_groups=GE, peer_barrier=not args.nccl_barrier,
                           copy_engine=args.exchange == "copy")
-    G = ens.n_groups
+    GE = ens.n_groups
+    DEVG = G > 1                      # device-timed step by groups?
+    G = GE if DEVG else 1
     I_host = make_indices(rng, args.dist, NT, NROWS, BAG, BATCH)
     idx_pinned = E.pinned_empty((BAG, BATCH, NT), np.int64)
     idx_pinned[...] = I_host
@@ -562,20 +567,20 @@ def run_sharded(args, rank, world, local):
     IDX_BESIDE = args.index_beside
 
     def step(events=None, pipelined=True):
-        ens.forward(I_dev, prefetch_index=IDX_BESIDE == "forward")
+        ens.forward(I_dev, prefetch_index=IDX_BESIDE == "forward", grouped=DEVG)
         n = ens.launches + (1 if ens.peer_barrier else 0)
         if events: events[1].record()
         if IDX_BESIDE == "exchange":
-            ens.prefetch_index()
+            ens.prefetch_index(DEVG)
         if pipelined:      # backward exchange and update!, table group by table group
-            ens.backward_update_(opt, delta_dev)
+            ens.backward_update_(opt, delta_dev, grouped=DEVG)
             n += ens.update_launches + ens.index_launches + 2 * G
             if events: events[2].record(); events[3].record()
         else:
             grads = ens.backward(delta_dev)
             n += 2
             if events: events[2].record()
-            ens.update_(opt, grads)
+            ens.update_(opt, grads, grouped=DEVG)
             n += lib.etb_last_launch_count() * G + ens.index_launches
             if events: events[3].record()
         launches[0] = n
@@ -650,7 +655,7 @@ def run_sharded(args, rank, world, local):
         if DUPLEX:
             upload_indices(1 - slot)                       # next step's indices: first in the H2D queue
         for c in range(E2E_CHUNKS):
-            ens.forward(I_buf[slot], cols=(cb[c], cb[c + 1]), prefetch_index=(c == 0))
+            ens.forward(I_buf[slot], cols=(cb[c], cb[c + 1]), prefetch_index=(c == 0), grouped=True)
             done = main.record_event()
             with torch.cuda.stream(d2h_stream):
                 d2h_stream.wait_event(done)
@@ -666,7 +671,7 @@ def run_sharded(args, rank, world, local):
         t0 = cb[E2E_DENSE]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_stream(d2h_stream)            # the host has the whole result before the rest of the cotangent exists
-            for g in range(G):
+            for g in range(GE):
                 for o in range(world):
                     r0 = plan.row_off[o] + ens.group_rows[o][g][0]
                     r1 = r0 + ens.group_rows[o][g][1]
@@ -675,7 +680,7 @@ def run_sharded(args, rank, world, local):
                     delta_dev.rows(r0, r1).cols(t0, plan.my_cols).upload(delta_pinned[r0:r1, t0:])
                 landed.append(copy_stream.record_event())
         ens.update_launches = 0
-        for g in range(G):
+        for g in range(GE):
             main.wait_event(landed[g])
             ens.scatter_group(delta_dev, g)
             ens.update_group_(opt, g)
@@ -752,7 +757,7 @@ def run_sharded(args, rank, world, local):
                     "d2h_bytes_per_step": int(out_pinned.nbytes),
                     "pipeline": ("indices double-buffered; forward in %d column chunks with overlapped D2H; cotangent: the first %d column "
                                  "chunks each right behind its own result chunk (full duplex), the rest in %d table-group row slices, each "
-                                 "group's exchange + update! as its slice lands" % (E2E_CHUNKS, E2E_DENSE, G))
+                                 "group's exchange + update! as its slice lands" % (E2E_CHUNKS, E2E_DENSE, GE))
                                 if fused else "plain chain"},
             "gpu_launches": launches[0] * K, "clocks": clocks.result,
             "roofline": {"bound": "hbm", "kernel": "pooled_kernel+a2a (fwd phase, max over ranks)",

@@ -147,6 +147,10 @@ class ShardedEnsemble:
             self.group_rows.append([(int(offs[b[g]]), int(offs[b[g + 1]] - offs[b[g]])) for g in range(G)])
         self.n_groups = G
         self.group_indexers = [Indexer() for _ in range(G)] if G > 1 else [self.indexer]
+        # an ensemble built with table groups can still be driven whole (one index!, one exchange, one update!): the
+        # `grouped` argument of prefetch_index / forward / update_ / backward_update_ chooses per call (bench.py: the
+        # device-timed step runs whole, the host-buffer step by groups); None = by groups iff there are groups
+        self._index_grouped = G > 1
         self._upd_stream = None
         self._I = None
         self._rows = (C.c_int64 * p.world)(*p.rows)
@@ -350,26 +354,30 @@ class ShardedEnsemble:
         per = bag * p.batch_global
         return [DeviceArray(glob, shape, t * per, None, np_dtype) for t in range(t_mine)]
 
-    def prefetch_index(self):
+    def prefetch_index(self, grouped=None):
         """index! of my tables for the indices of the last forward(), on the side stream, starting behind whatever the
         current stream holds so far.  forward() calls it before the lookup (index! then runs beside the lookup, both
         HBM-bound); called after forward(..., prefetch_index=False) it runs beside the backward exchange instead, which
         is NVLink-bound and leaves HBM idle."""
         p = self.plan
         self.index_launches = 0
+        self._index_grouped = (self.n_groups > 1) if grouped is None else (bool(grouped) and self.n_groups > 1)
+        if not self._index_grouped:
+            _prefetch_index(self.indexer, self.tables, self._I)
+            self.index_launches = _lib.lib().etb_last_launch_count()
+            return
         b = self.group_bounds[p.rank]
         for g, ix in enumerate(self.group_indexers):
-            a0, a1 = (b[g], b[g + 1]) if self.n_groups > 1 else (0, len(self.tables))
-            _prefetch_index(ix, self.tables[a0:a1], self._I[a0:a1])
+            _prefetch_index(ix, self.tables[b[g]:b[g + 1]], self._I[b[g]:b[g + 1]])
             self.index_launches += _lib.lib().etb_last_launch_count()
 
-    def forward(self, I, out: DeviceArray = None, prefetch_index: bool = True, cols=None) -> DeviceArray:
+    def forward(self, I, out: DeviceArray = None, prefetch_index: bool = True, cols=None, grouped=None) -> DeviceArray:
         p = self.plan
         Is = [as_device_indices(i) for i in (I if isinstance(I, (list, tuple)) else
                                              [I.lastdim(t) for t in range(I.shape[-1])])]
         self._I = Is
         if prefetch_index:   # index! needs only the indices: run it beside the lookup and the exchange
-            self.prefetch_index()
+            self.prefetch_index(grouped)
         if self.fused:
             assert out is None, "fused mode writes into the peer-mapped self.out"
             if self.copy_engine and cols is None:
@@ -421,8 +429,10 @@ class ShardedEnsemble:
             off += f
         return grads
 
-    def update_(self, opt, grads):
-        if self.n_groups == 1:
+    def update_(self, opt, grads, grouped=None):
+        if grouped is None:
+            grouped = self._index_grouped    # whichever Indexers the last prefetch filled (update_ re-indexes otherwise)
+        if self.n_groups == 1 or not grouped:
             update_(opt, self.tables, grads, [self.indexer])
             return
         b = self.group_bounds[self.plan.rank]
@@ -452,12 +462,14 @@ class ShardedEnsemble:
     def join_updates(self):
         torch.cuda.current_stream().wait_stream(self._upd_stream)
 
-    def backward_update_(self, opt, delta: DeviceArray):
+    def backward_update_(self, opt, delta: DeviceArray, grouped=None):
         """backward + update!, pipelined over table groups (fused mode): while the owners update group g the
         cotangent of group g+1 crosses NVLink.  Same results as backward() followed by update_()."""
         self.update_launches = 0
-        if not self.fused or self.n_groups == 1:
-            self.update_(opt, self.backward(delta))
+        if grouped is None:
+            grouped = self._index_grouped
+        if not self.fused or self.n_groups == 1 or not grouped:
+            self.update_(opt, self.backward(delta), grouped=False)
             self.update_launches = _lib.lib().etb_last_launch_count()
             return
         for g in range(self.n_groups):

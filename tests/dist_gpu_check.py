@@ -51,15 +51,17 @@ plan = ShardPlan(dims, world, rank, prepend, batch)
 mine = list(plan.my_tables)
 # NCCL all-to-all + pack/unpack; NVLink peer stores + NCCL barrier; peer stores + flag barrier + pipelined backward
 # ...; the same with the copy engines carrying the blocks
-for fused, groups, peer_barrier, copy_engine in ((False, 1, False, False), (True, 1, False, False), (True, 3, True, False),
-                                                 (True, 1, True, True)):
+# ...; an ensemble built with table groups but driven whole (grouped=False: one index!, one exchange, one update!)
+for fused, groups, peer_barrier, copy_engine, grouped in ((False, 1, False, False, None), (True, 1, False, False, None),
+                                                          (True, 3, True, False, None), (True, 1, True, True, None),
+                                                          (True, 3, True, False, False)):
     ens = ShardedEnsemble([make_table(t) for t in mine], plan, fused=fused, table_groups=groups, peer_barrier=peer_barrier,
                           copy_engine=copy_engine)
     ens.out.fill(-5.0)
     torch.cuda.synchronize()
     dist.barrier()
     for rep in range(2):        # twice: buffers are reused across steps
-        out = ens.forward([I[t] for t in mine])
+        out = ens.forward([I[t] for t in mine], grouped=grouped)
         got = out.numpy()
         want = orc_out[:, plan.clo[rank]:plan.chi[rank]]
         assert np.array_equal(got[prepend:], want[prepend:]), f"sharded forward differs from the oracle (fused={fused}, copy_engine={copy_engine})"
@@ -67,8 +69,8 @@ for fused, groups, peer_barrier, copy_engine in ((False, 1, False, False), (True
         d_local = E.DeviceArray.from_numpy(delta[:, plan.clo[rank]:plan.chi[rank]])
         if rep == 0:
             grads = ens.backward(d_local)
-        elif groups > 1:        # update once, after the second (buffer-reusing) round trip: group by group
-            ens.backward_update_(E.Descent(0.1), d_local)
+        elif groups > 1:        # update once, after the second (buffer-reusing) round trip: group by group (or whole)
+            ens.backward_update_(E.Descent(0.1), d_local, grouped=grouped)
         else:
             ens.update_(E.Descent(0.1), ens.backward(d_local))
     for t, tab in zip(mine, ens.tables):
@@ -89,5 +91,5 @@ for wire in (None, np.int32):
 torch.cuda.synchronize()
 dist.barrier()
 if rank == 0:
-    print("dist check ok", world, "(sharded == single GPU == oracle, bit for bit: NCCL, fused + NCCL barrier, fused + peer-flag barrier + grouped backward, copy engines)")
+    print("dist check ok", world, "(sharded == single GPU == oracle, bit for bit: NCCL, fused + NCCL barrier, fused + peer-flag barrier + grouped backward, copy engines, grouped ensemble driven whole)")
 dist.destroy_process_group()

@@ -123,7 +123,8 @@ def main():
     for d in jl("r2_c4_n8.jsonl"):
         A(f"| {d['batch_global']} | {d['dist']} | {d['ms_per_step']:.2f} | {d['lookups_per_sec'] / 1e9:.1f} | {d['fwd_lookup+exchange_ms']:.2f} ms ({d['fwd_frac_of_measured_hbm_peak']:.2f}) | {d['bwd_exchange_alone_ms']:.3f} ms | {d['bwd_exchange_gbs_per_gpu']:.0f} ({d['bwd_exchange_frac_of_nvlink']:.2f}) |")
     A("\n(Measured in the first half of round 2, before the hot rows were sliced: the Zipf runs use the strict order with one CTA per hot row.  "
-      "e2e at N = 2 varies between boxes: 9.7 ms on this one, 12.8 ms on another.)\n")
+      "e2e at N = 2 varies between boxes (9.7 - 12.9 ms with the same code); on the box of the committed line the host-buffer step by 4 table groups "
+      "(`ETB_E2E_TABLE_GROUPS`, the default) takes 11.7 ms, 12.9 ms with the ensemble whole, 11.7 ms with 7 groups.)\n")
     if os.path.exists(os.path.join(P, "r2_pcie_probe_n8.json")):
         p1, p8 = last("r2_pcie_probe_n1.json"), last("r2_pcie_probe_n8.json")
         p2 = last("r2_pcie_probe_n2.json") if os.path.exists(os.path.join(P, "r2_pcie_probe_n2.json")) else None
