@@ -54,7 +54,7 @@ def main():
     A("| `r2_bench_c2_uniform.json`, `r2_bench_c2_zipf_strict.json` | `python bench.py --steps 20 --warmup 5` / `--dist zipf`: the bench lines (strict = the default update order); `r2_bench_c2_uniform_e2e_serial.json`: the same with `ETB_E2E_DUPLEX=0` (the whole result on the host before any cotangent is sent) |")
     A("| `r2_launches_bench_c2.csv`, `r2_launches_c3_strict.csv` | `ncu --metrics gpu__time_duration.sum --clock-control none` launch lists of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` and of `tools/c3_once.py` (C3, strict order) |")
     A("| `r2_ncu_kernels.json` | per-launch DRAM bytes / time / registers / occupancy / issue utilisation of the hot kernels from `ncu --set full` captures of the same program (`bench.py` reads `roofline.traffic` from it) |")
-    A("| `r2_bench_c2_n2.json`, `r2_bench_c2_n8.json` | torchrun bench lines at N = 2 / 8 (one table group = the default); `..._2groups`, `..._4groups`: the table-group pipelined backward |")
+    A("| `r2_bench_c2_n2.json`, `r2_bench_c2_n4.json`, `r2_bench_c2_n8.json` | torchrun bench lines at N = 2 / 4 / 8 (one table group = the default); `..._2groups`, `..._4groups`: the table-group pipelined backward |")
     A("| `r2_dist_check_n2.log`, `r2_dist_check_n8.log`, `r2_bench_c2_n8_selfcheck.log` | `tests/dist_gpu_check.py` under torchrun (sharded == single GPU == ORACLE, bit for bit, three exchange modes) and the per-rank self-check lines of `bench.py --gpus 8` |")
     A("| `r2_c4_n8.jsonl` | `tools/bench_c4.py` on 8 GPUs: BASELINE configs[3] (64 chunked tables of 5 M rows) |")
     A("| `r2_index.jsonl`, `r2_index_rank0.jsonl` | `tools/index_bench.py`: index! alone by CUDA-graph replay at the C1–C4 shapes, records checked against numpy's stable sort; `rank0` = the all-ballots ranking |")
@@ -103,7 +103,11 @@ def main():
     A("## Multi-GPU (weak scaling: 26 tables per GPU, global batch 16384, fused NVLink exchange, peer-memory barrier)\n")
     A("| N | ms/step (device, max over ranks) | G lookups/s | lookup + exchange | backward exchange | index! + update! | e2e ms/step | round 1 |\n|---|---|---|---|---|---|---|---|")
     A(f"| 1 | {b['ms_per_step']:.2f} | {b['value'] / 1e9:.2f} | {k['pooled_kernel']['ms']:.2f} | - | {k[ix_name]['ms'] + k['sgd_update_kernel']['ms']:.2f} | {b['e2e']['ms_per_step']:.1f} | 3.39 / 9.0 |")
-    for d, r1s in ((n2, "3.58 / 15.6"), (n8, "3.72 / 38.8")):
+    rows_n = [(n2, "3.58 / 15.6")]
+    if os.path.exists(os.path.join(P, "r2_bench_c2_n4.json")):
+        rows_n.append((last("r2_bench_c2_n4.json"), "3.66 / 26.9"))
+    rows_n.append((n8, "3.72 / 38.8"))
+    for d, r1s in rows_n:
         ph = d["phases_ms"]
         A(f"| {d['n_gpus']} | {d['ms_per_step']:.2f} | {d['value'] / 1e9:.2f} | {ph['fwd_lookup+exchange']:.2f} | {ph['bwd_exchange']:.2f} | {ph['index+update']:.2f} | {d['e2e']['ms_per_step']:.1f} | {r1s} |")
     A(f"\nWeak-scaling efficiency at N = 8: {b['ms_per_step'] / n8['ms_per_step']:.2f} (device-timed).  Self-check before timing: `{n8['self_check']}` "
