@@ -34,3 +34,33 @@ def test_reference_arm_nonzero_ranks_do_nothing():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_clock_sampler_keeps_only_the_timed_regions(tmp_path, monkeypatch):
+    """bench.py starts nvidia-smi when the process starts (its first sample takes seconds on an 8-GPU box) and reports
+    only the samples stamped inside the timed regions: a fake nvidia-smi that idles at 210 MHz, then runs at 1965 MHz
+    with the power cap active, must give the latter."""
+    import stat
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("""#!/usr/bin/env python3
+import datetime, sys, time
+t0 = time.time()
+while True:
+    busy = time.time() - t0 > 0.6
+    now = datetime.datetime.now().strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    print(f"{now}, 0, {1965 if busy else 210}, 1965, 500.0, 0x4, Not Active, Not Active, Not Active, {'Active' if busy else 'Not Active'}", flush=True)
+    time.sleep(0.02)
+""")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    sys.path.insert(0, ROOT)
+    import bench
+    cs = bench.ClockSampler(0).start()
+    time.sleep(0.8)                      # set-up: idle clocks, must not be reported
+    cs.mark_begin()
+    time.sleep(0.4)                      # "timed regions"
+    cs.stop()
+    r = cs.result
+    assert r["sm_mhz"] == 1965.0 and r["sm_max_mhz"] == 1965.0 and r["reasons"] == ["sw_power_cap"]
+    assert r["samples"] >= 5 and r["window"] == "timed regions"
