@@ -1,18 +1,14 @@
-// etb_update.cu -- K4 index! (sort + segment) and K5 fused segment-reduce + SGD (sm_100a).
+// etb_update.cu -- K5 fused segment-reduce + SGD over the buckets of index!, the a2a helpers, the host-tier cache (sm_100a).
 //
-// Replaces the reference's Indexer (histogram!/prefixsum!/remap!, src/utils.jl:131-314 -- a
-// stable counting sort of occurrence -> delta column by table row) and its update! kernels
-// (src/sparseupdate.jl:57-154, ensemble form :199-238).
+// Replaces the reference's update! kernels (src/sparseupdate.jl:57-154, ensemble form :199-238), which walk the
+// buckets of its Indexer (histogram!/prefixsum!/remap!, src/utils.jl:131-314: a stable counting sort of
+// occurrence -> delta column by table row).
 //
-// K4.  Every occurrence p of item t becomes the pair
-//          key = t << row_bits | (index - 1),      value = delta column of p (= p / bag)
-// All items are sorted at once by a hand-written stable LSD radix sort restricted to the bits the
-// keys actually use (etb_sort.cuh), so members of a bucket stay in occurrence order = the order
-// remap! records (src/utils.jl:242-272).  Bucket starts are the positions whose key differs from the previous one,
-// compacted into one 16-byte record per bucket by three small hand-written kernels (count heads per
-// tile, scan the tile counts, write records).  Buckets come out in ascending (table, row) order instead
-// of the reference's first-seen order; buckets are disjoint table rows, so results do not
-// depend on that order.
+// K4 (index!) lives in etb_index.cu / etb_index.cuh: a per-table segmented, stable LSD radix sort of
+// (row, delta column) pairs and one 16-byte record per bucket (start, first delta column, slot << row_bits | row).
+// Members of a bucket stay in occurrence order = the order remap! records (src/utils.jl:242-272); buckets come
+// out in ascending (table, row) order instead of the reference's first-seen order -- buckets are disjoint table
+// rows, so results do not depend on that order.
 //
 // K5.  A group of G lanes owns one bucket: acc = 0; acc += delta[:, map[i]] for the bucket's
 // members in order (one lane per feature vector, like the lookup kernels, so the sum has the
@@ -21,9 +17,11 @@
 // (:88) -- a per-table choice, like the reference's dispatch.  One bucket = one row = one writer:
 // no atomics touch table data.  Kernels: sgd_update_exact_kernel / sgd_update_kernel (a warp per
 // tile of 32 buckets; buckets of up to 4 members finish here), bucket_tasks_kernel (buckets of 5..128
-// members and the 128-member chunks of longer ones), long_combine_kernel (chunk partials of a long
-// bucket, added in a fixed order).  The only atomics are worklist cursors; nothing that reaches a
-// result depends on their order.
+// members and, in the opt-in split order, the 128-member chunks of longer ones), long_strict_sliced_kernel
+// (strict order, the default: a bucket of more than 128 members is cut into slices of 16 feature elements,
+// every slice streamed and added on its own SM; long_strict_kernel, one CTA per bucket, for Adagrad),
+// long_combine_kernel (split order: chunk partials of a long bucket, added in a fixed order).  The only
+// atomics are worklist cursors; nothing that reaches a result depends on their order.
 #include <algorithm>
 #include <type_traits>
 #include <vector>
