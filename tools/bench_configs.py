@@ -111,11 +111,24 @@ def config_c1(fh):
         with torch.cuda.graph(g, stream=s):
             step()
     t_graph = timeit(g.replay, flush=flush)
+
+    def step_par():      # index! needs only the indices: on the side stream beside the gather (two branches in the graph)
+        E.prefetch_index(indexer, tables, Is)
+        fwd()
+        E.update_(opt, tables, grads, [indexer])
+
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        step_par(); torch.cuda.synchronize()
+        with torch.cuda.graph(g2, stream=s):
+            step_par()
+    t_graph_par = timeit(g2.replay, flush=flush)
     u = sum(int(np.unique(i.numpy()).size) for i in Is)
     fwd_bytes = nt * batch * (8 + 2 * dim * 4)
     upd_bytes = nt * (batch * 8 + batch * dim * 4) + 2 * u * dim * 4
     emit({"config": "C1", "shape": f"{nt} x ({dim} x {nrows}) f32, batch {batch}, gather + update!",
           "fwd_us": t_fwd * 1e3, "update_us": t_upd * 1e3, "step_us": t_step * 1e3, "step_cuda_graph_us": t_graph * 1e3,
+          "step_cuda_graph_index_beside_gather_us": t_graph_par * 1e3,
           "lookups_per_step": nt * batch, "lookups_per_sec_graph": nt * batch / (t_graph * 1e-3),
           "fwd_gbs": fwd_bytes / t_fwd / 1e6, "update_gbs": upd_bytes / t_upd / 1e6,
           "roofline_time_us_at_measured_peak": (fwd_bytes + upd_bytes) / PEAK / 1e3,

@@ -142,7 +142,7 @@ def main():
           f"{tot / (p8['h2d']['gbs_aggregate'] * 1e6):.1f} ms one direction at a time; measured {n8['e2e']['ms_per_step']:.1f} ms.\n")
     A("## Other configs on one GPU\n")
     c1 = last("r2_c1_gather_update.jsonl")
-    A(f"* **C1** (26 x (64 x 100k), batch 2048, gather + update!): one CUDA graph {c1['step_cuda_graph_us']:.0f} µs (round 1: 86; roofline {c1['roofline_time_us_at_measured_peak']:.1f} µs); eager through the Python mirror {c1['step_us']:.0f} µs; index! 2 launches, 20 µs (`ix_small_kernel`).")
+    A(f"* **C1** (26 x (64 x 100k), batch 2048, gather + update!): one CUDA graph {c1['step_cuda_graph_us']:.0f} µs ({c1.get('step_cuda_graph_index_beside_gather_us', float('nan')):.0f} µs with index! on the side stream beside the gather; round 1: 86; roofline {c1['roofline_time_us_at_measured_peak']:.1f} µs; 7 graph nodes of 6 – 7 µs each: launch latency, not traffic); eager through the Python mirror {c1['step_us']:.0f} µs; index! 2 launches, 20 µs (`ix_small_kernel`).")
     A("* **C3** (one 128 x 10M table, Zipf(1.05), `r2_c3_zipf_update.jsonl`; GPU time by graph replay, index! + update kernels):\n")
     A("| form | n | hottest row | order | update µs | of which index! | algorithmic GB/s (frac of measured peak) | before the slicing | round 1 (eager) |\n|---|---|---|---|---|---|---|---|---|")
     uns = {(d['form'], d['n'], d['order']): d for d in jl("r2_c3_zipf_update_unsliced.jsonl")} if os.path.exists(os.path.join(P, "r2_c3_zipf_update_unsliced.jsonl")) else {}
