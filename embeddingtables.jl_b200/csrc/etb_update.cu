@@ -1313,6 +1313,31 @@ static UpdClass classify_update(const etb_update_item& it) {
 
 enum { kKernelMain = 0, kKernelTasks = 1, kKernelCombine = 2, kKernelStrictLong = 3 };
 
+// fork / join of the task kernel (update_impl): one side stream and two events per host thread and device
+struct ForkJoin {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static ForkJoin* fork_join() {
+    static thread_local ForkJoin fj[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    ForkJoin& f = fj[dev];
+    if (!f.side) {
+        if (cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming) != cudaSuccess) {
+            f.side = nullptr;
+            return nullptr;
+        }
+    }
+    return &f;
+}
+static bool update_fork_enabled() {
+    static const bool on = [] { const char* e = getenv("ETB_UPDATE_FORK"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 // ETB_STRICT_SLICED=0: round 2's one-CTA-per-bucket kernel for the long buckets of the strict order (kept for comparison)
 static bool strict_sliced() {
     static const bool on = [] { const char* e = getenv("ETB_STRICT_SLICED"); return !(e && e[0] == '0'); }();
@@ -1496,12 +1521,21 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
         launch_update(opt, kKernelMain, c, grid, stream, P);
         ETB_LAUNCHED();
         const int64_t per_block = kUThreads / c.G;
-        if (view->n_total > kShortMax) {  // medium buckets + long-bucket chunks: one task kernel
+        // Strict order, SGD: the task kernel (buckets of 5..128 members) and the sliced long-bucket kernel work on
+        // disjoint buckets and both depend only on the main kernel's worklists, so the task kernel runs on an internal
+        // side stream beside the long buckets (a fork and a join of events: capturable, two parallel branches in a CUDA
+        // graph).  C3: the 45 us of tasks disappear behind the hottest row's chain.  ETB_UPDATE_FORK=0: one after the other.
+        ForkJoin* fj = (P.strict_long == 2 && view->n_total > kLongThreshold && update_fork_enabled()) ? fork_join() : nullptr;
+        auto launch_tasks = [&](cudaStream_t ts) -> int32_t {  // medium buckets + long-bucket chunks: one task kernel
             const int64_t max_tasks = view->n_total / (kShortMax + 1) + 1;
             const int gridT = (int)std::min<int64_t>((max_tasks + per_block - 1) / per_block, (int64_t)num_sms() * 8);
-            launch_update(opt, kKernelTasks, c, gridT, stream, P);
+            launch_update(opt, kKernelTasks, c, gridT, ts, P);
             ETB_LAUNCHED();
-        }
+            return ETB_OK;
+        };
+        if (fj) ETB_CUDA(cudaEventRecord(fj->fork, stream));  // behind the main kernel
+        if (!fj && view->n_total > kShortMax)
+            if (int32_t st = launch_tasks(stream)) return st;
         if (P.strict_long && view->n_total > kLongThreshold) {
             const int64_t max_long = view->n_total / kLongThreshold + 1;
             const int64_t nsl = sliced ? ((int64_t)c.nvec * c.vb / (int64_t)elt_bytes(c.elt) + kSliceElems - 1) / kSliceElems : 1;
@@ -1509,12 +1543,18 @@ static int32_t update_impl(const etb_index_view* view, const etb_update_item* it
             launch_update(opt, kKernelStrictLong, c, gridS, stream, P);
             ETB_LAUNCHED();
         }
+        if (fj) {  // the long buckets were launched first: their CTAs take the SMs, the tasks fill in as the short jobs end
+            ETB_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+            if (int32_t st = launch_tasks(fj->side)) return st;
+            ETB_CUDA(cudaEventRecord(fj->join, fj->side));
+        }
         if (P.split_long && view->n_total > kLongThreshold) {
             const int64_t max_long = view->n_total / kLongThreshold + 1;
             const int gridB = (int)std::min<int64_t>(max_long, (int64_t)num_sms() * 4);  // one CTA per long bucket
             launch_update(opt, kKernelCombine, c, gridB, stream, P);
             ETB_LAUNCHED();
         }
+        if (fj) ETB_CUDA(cudaStreamWaitEvent(stream, fj->join, 0));  // the caller's stream continues behind both kernels
         i0 += n;
     }
     return ETB_OK;
